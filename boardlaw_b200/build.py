@@ -1,0 +1,82 @@
+"""Builds ``boardlaw_b200/libboardlaw_b200.so`` in-tree with nvcc for sm_100a.
+
+No torch headers are involved: the library is a plain C-ABI shared object (``include/boardlaw_b200.h``).
+nvcc cross-compiles without a GPU, so this runs in the build container; the resulting ``.so`` is
+git-ignored but travels to the GPU box with the snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / 'csrc'
+OBJ = HERE / 'csrc' / '_obj'
+LIB = HERE / 'libboardlaw_b200.so'
+
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
+          '--expt-relaxed-constexpr']
+
+# per-file extra flags.  mcts.cu holds the bit-exact fp32 arithmetic (no FMA contraction, IEEE
+# division/sqrt, denormals kept) — see DESIGN.md "arithmetic contract".
+SOURCES = {
+    'hex.cu': [],
+    'mcts.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
+    'engine.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
+    'net.cu': [],
+    'host.cu': [],
+}
+
+
+def nvcc():
+    exe = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not Path(exe).exists():
+        raise RuntimeError('nvcc not found: the boardlaw_b200 kernels cannot be built')
+    return exe
+
+
+def _stale(target, deps):
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    OBJ.mkdir(exist_ok=True)
+    headers = list(CSRC.glob('*.cuh')) + [HERE.parent / 'include' / 'boardlaw_b200.h', Path(__file__)]
+    objs, procs = [], []
+    for name, extra in SOURCES.items():
+        src = CSRC / name
+        if not src.exists():
+            continue
+        obj = OBJ / (src.stem + '.o')
+        objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc()] + ARCH + COMMON + extra + ['-Xptxas', '-v', '-c', str(src), '-o', str(obj)]
+            if verbose:
+                print(' '.join(cmd))
+            procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for name, p in procs:
+        out, _ = p.communicate()
+        (OBJ / (Path(name).stem + '.ptxas.log')).write_text(out)
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(out)
+        elif verbose:
+            print(out)
+    if failed:
+        raise RuntimeError('nvcc failed')
+    if force or procs or _stale(LIB, objs):
+        cmd = [nvcc()] + ARCH + ['-shared', '-o', str(LIB)] + [str(o) for o in objs] + ['-cudart', 'static']
+        if verbose:
+            print(' '.join(cmd))
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='-f' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,212 @@
+/*
+ * boardlaw_b200 — C ABI of the B200-native (sm_100a) Hex / MCTS / policy-value-net hot path.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain device
+ * pointers, sizes and a CUDA stream (as void*), never allocates or frees device memory,
+ * never synchronises, and returns the cudaError_t of its last launch (0 = success,
+ * negative = argument error detected on the host).  All launches are CUDA-graph capturable.
+ *
+ * Each function cites the reference interface (andyljones/boardlaw) it replaces.  The
+ * reference binds these through pybind11 torch extensions; the ctypes binding a maintainer
+ * would add is shown in INTEGRATION.md and implemented in boardlaw_b200/_lib.py.
+ *
+ * Layout conventions (all tensors contiguous, row-major):
+ *   B = n_envs, T = n_nodes, S = boardsize, A = S*S actions, Sn = n_seats (2 for Hex)
+ *   "half" arguments are IEEE binary16 bit patterns (uint16_t here, __half on the device).
+ */
+#ifndef BOARDLAW_B200_H
+#define BOARDLAW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t bl_half;
+typedef void *bl_stream;
+
+/* ABI version, bumped on any signature change. */
+int bl_abi_version(void);
+
+/* Selects the CUDA device for subsequent launches from the calling thread (the library links the CUDA
+ * runtime statically; replaces the CUDAGuard of boardlaw/hex/cpp/cuda.cu:140, boardlaw/mcts/cpp/cuda.cu:121). */
+int bl_set_device(int device);
+
+/* Fills out[65536] (HOST memory) with expf() of every binary16 bit pattern as evaluated by
+ * the host libm — the table the descend kernels index so that exp(logit) is identical to the
+ * value the reference's CPU build obtains from libm (boardlaw/mcts/cpp/cpu.cpp:89).  The
+ * caller uploads it once per device and passes it as `exp_lut`. */
+void bl_exp_table_host(float *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Hex — replaces hexcuda.step / hexcuda.observe (boardlaw/hex/cpp/wrappers.cpp:39-40,
+ * kernels boardlaw/hex/cpp/cuda.cu:76-152 and :154-217).
+ * ------------------------------------------------------------------------------------------- */
+
+/* In place on board (B,S,S) u8.  rewards (B,2) f32 is fully written (zeros unless a win). */
+int bl_hex_step(uint8_t *board, const int32_t *seats, const int32_t *actions, float *rewards,
+                int B, int S, bl_stream stream);
+
+/* obs (B,S,S,2) f32, fully written.  B is the product of all leading batch dims. */
+int bl_hex_observe(const uint8_t *board, const int32_t *seats, float *obs, int B, int S,
+                   bl_stream stream);
+
+/* Fused env transition = Hex.step of boardlaw/hex/__init__.py:161-195 without the host syncs:
+ * copies board->new_board, applies the move, auto-resets finished games (board and seat zeroed),
+ * flips the seat, and records rule violations (negative / out-of-range / occupied cell) by
+ * OR-ing bits into *error_word instead of asserting on the host.
+ * terminal (B,) u8 (bool), rewards (B,2) f32.  reset!=0 mirrors `reset=True`. */
+int bl_hex_transition(const uint8_t *board, const int32_t *seats, const int64_t *actions,
+                      uint8_t *new_board, int32_t *new_seats, float *rewards, uint8_t *terminal,
+                      int32_t *error_word, int reset, int B, int S, bl_stream stream);
+
+/* valid (B,A) u8 (bool) in the mover's frame = (obs == 0).all(-1) of boardlaw/hex/__init__.py:154-159,
+ * computed from the board without materialising obs. */
+int bl_hex_valid(const uint8_t *board, const int32_t *seats, uint8_t *valid, int B, int S,
+                 bl_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MCTS ops on the reference's tensor layout — replace mctscuda.descend / root / backup
+ * (boardlaw/mcts/cpp/wrappers.cpp:52-73; kernels boardlaw/mcts/cpp/cuda.cu:101-248).
+ *   logits (B,T,A) half, w (B,T,Sn) half, n (B,T) i16, c_puct (B,) half, seats (B,T) i16,
+ *   terminal (B,T) bool, children (B,T,A) i16.
+ * `qrange` is 2 floats of device scratch that receive (min, max) of w/(n+1e-4) over the whole
+ * batch (transition_q, cuda.cu:101-105).  `exp_lut` is the uploaded bl_exp_table_host table.
+ * `counters` (optional, may be NULL) is 4 x uint64 on the device, incremented by: policy
+ * evaluations, existing children seen, Newton iterations, descents.
+ * ------------------------------------------------------------------------------------------- */
+
+/* rands (B,T) half is the tensor the reference draws with at::rand_like inside descend
+ * (cuda.cu:191); here the caller draws it.  parents, actions (B,) i16 out. */
+int bl_mcts_descend(const bl_half *logits, const bl_half *w, const int16_t *n, const bl_half *c_puct,
+                    const int16_t *seats, const uint8_t *terminal, const int16_t *children,
+                    const bl_half *rands, const float *exp_lut, float *qrange,
+                    int16_t *parents, int16_t *actions, uint64_t *counters,
+                    int B, int T, int A, int Sn, bl_stream stream);
+
+/* probs (B,A) half out: the regularised policy at node 0 (cuda.cu:107-136). */
+int bl_mcts_root(const bl_half *logits, const bl_half *w, const int16_t *n, const bl_half *c_puct,
+                 const int16_t *seats, const uint8_t *terminal, const int16_t *children,
+                 const float *exp_lut, float *qrange, bl_half *probs,
+                 int B, int T, int A, int Sn, bl_stream stream);
+
+/* In place on n (B,T) i16 and w (B,T,Sn) half (cuda.cu:205-248).  leaves (B,) i16. */
+int bl_mcts_backup(const bl_half *v, bl_half *w, int16_t *n, const bl_half *rewards,
+                   const int16_t *parents, const uint8_t *terminal, const int16_t *leaves,
+                   int B, int T, int Sn, bl_stream stream);
+
+/* transition_q alone (cuda.cu:101-105): q (B,T,Sn) half out, qrange as above. */
+int bl_mcts_transition_q(const bl_half *w, const int16_t *n, bl_half *q, float *qrange,
+                         int B, int T, int Sn, bl_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Policy/value network — replaces FCModel.forward (boardlaw/networks.py:37-41) with the heads of
+ * boardlaw/heads.py:41-52 (TensorIntake), :93-104 (MaskedOutput), :128-142 (ValueOutput) and the
+ * ReZero residual blocks of boardlaw/networks.py:10-18.  The observation is never materialised:
+ * the kernels read the board and the seat.
+ *
+ * Weights are the fp32 tensors of the reference's state_dict (body.0.*, body.k.*, policy.core.*,
+ * value.core.*), contiguous, on the device.
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct bl_fc_params {
+    int S;            /* boardsize                                                             */
+    int W;            /* width                                                                 */
+    int D;            /* number of ReZero residual blocks                                      */
+    int precision;    /* 0: fp32-accurate (exact fp32 products or split-fp16 tensor-core products,
+                            fp32 accumulation); 1: fp16 operands / fp32 accumulation (mirrors the
+                            reference's autocast, boardlaw/mcts/__init__.py:131-133)               */
+    const float *w_in;    /* (W, 2A)  body.0.weight       */
+    const float *b_in;    /* (W,)     body.0.bias         */
+    const float *w_res;   /* (D, W, W) body.k.weight      */
+    const float *b_res;   /* (D, W)   body.k.bias         */
+    const float *alpha;   /* (D,)     body.k.α            */
+    const float *w_pol;   /* (A, W)   policy.core.weight  */
+    const float *b_pol;   /* (A,)     policy.core.bias    */
+    const float *w_val;   /* (W,)     value.core.weight   */
+    const float *b_val;   /* (1,)     value.core.bias     */
+    const void *packed;   /* tensor-core operand blob built by bl_fc_pack (NULL: CUDA-core path)   */
+} bl_fc_params;
+
+/* Bytes of device scratch bl_fc_forward needs for a batch of B envs. */
+int64_t bl_fc_scratch_bytes(const bl_fc_params *p, int B);
+
+/* board (B,S,S) u8, seats (B,) i32 -> logits (B,A) f32 (masked log-softmax, -inf on occupied cells),
+ * v (B,2) f32 with v[seat]=tanh(.), v[1-seat]=-tanh(.). */
+int bl_fc_forward(const bl_fc_params *p, const uint8_t *board, const int32_t *seats,
+                  float *logits, float *v, void *scratch, int B, bl_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused search engine — the whole of MCTS.initialize / simulate / root
+ * (boardlaw/mcts/__init__.py:72-149) on a persistent, privately laid out workspace.
+ * The workspace arrays are allocated by the caller (torch) and described by bl_tree.
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct bl_tree {
+    int B, T, S, A, Sn;
+    int AP;               /* row pitch of pi in floats (A rounded up to a multiple of 4)            */
+    int BP;               /* row pitch of board in bytes (A rounded up to a multiple of 16)         */
+    float *pi;            /* (B,T,AP) exp(logits) as fp32, value of exp_lut[half(logit)]             */
+    bl_half *logits;      /* (B,T,A) half or NULL: reference-layout mirror (kept only in debug mode) */
+    uint8_t *board;       /* (B,T,BP) u8 absolute-frame boards                                      */
+    uint8_t *seats;       /* (B,T)  u8 seat to move                                                 */
+    uint8_t *terminal;    /* (B,T)  u8                                                              */
+    int16_t *parents;     /* (B,T)  i16, -1 = none                                                  */
+    int16_t *relation;    /* (B,T)  i16 action that led here                                        */
+    int16_t *first_child; /* (B,T)  i16 head of the child list, -1 = none                           */
+    int16_t *next_sib;    /* (B,T)  i16 next sibling                                                */
+    int16_t *n;           /* (B,T)  i16 visit counts (incremented Sn per visit, as the reference)   */
+    bl_half *w;           /* (B,T,Sn) half                                                          */
+    bl_half *v;           /* (B,T,Sn) half                                                          */
+    bl_half *rewards;     /* (B,T,Sn) half                                                          */
+    bl_half *c_puct;      /* (B,)   half                                                            */
+    int16_t *leaf;        /* (B,)   i16 leaf of the current simulation                              */
+    int16_t *leaf_parent; /* (B,)   i16                                                             */
+    int16_t *leaf_action; /* (B,)   i16                                                             */
+    float *qrange;        /* (T+1,2) per-simulation (min,max) of w/(n+1e-4), ordered-int encoded    */
+    uint64_t *counters;   /* (8,) policy evals, children seen, newton iters, descents, backup nodes */
+    const float *exp_lut; /* (65536,)                                                               */
+} bl_tree;
+
+/* Resets the workspace for a new search rooted at (board (B,S,S) u8, seats (B,) i32). */
+int bl_tree_reset(const bl_tree *t, const uint8_t *board, const int32_t *seats, float c_puct,
+                  bl_stream stream);
+
+/* Writes the network evaluation of node `node` for every env: logits (B,A) f32 (or half if
+ * logits_are_half) and v (B,2), rounded to half exactly as `decisions.half()` does
+ * (boardlaw/mcts/__init__.py:135-136), stored as pi = exp_lut[half(logit)].
+ * node < 0 means "the current leaf of each env" (t->leaf). */
+int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, const void *v,
+                     int inputs_are_half, bl_stream stream);
+
+/* descend + expand + env step of simulation `sim` (boardlaw/mcts/__init__.py:108-129):
+ * writes t->leaf / leaf_parent / leaf_action, links new nodes, steps the parent's board into the
+ * leaf slot, records rewards / terminal.  rands: (B,T) half injected random numbers, or NULL to
+ * draw them in-kernel from Philox4x32-10 keyed by (seed, stream_id) and counted by (env, node). */
+int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed,
+                           uint64_t stream_id, bl_stream stream);
+
+/* backup of the current leaves (boardlaw/mcts/cpp/cuda.cu:205-248) + the q-range scan used by the next
+ * descent (transition_q's global min/max, cuda.cu:101-105), stored in qrange[sim+1]. */
+int bl_tree_backup(const bl_tree *t, int sim, bl_stream stream);
+
+/* Network evaluation of the current leaves straight into the tree (fused set_eval). */
+int bl_tree_eval_leaves(const bl_tree *t, const bl_fc_params *p, int sim, bl_stream stream);
+
+/* Root evaluation: logits f32 (B,A) and v f32 (B,2) of node 0 are returned to the caller, who mixes the
+ * Dirichlet noise (boardlaw/mcts/__init__.py:13-24) and hands the result to bl_tree_set_eval(node=0). */
+int bl_tree_eval_root(const bl_tree *t, const bl_fc_params *p, float *logits, float *v, bl_stream stream);
+
+/* Regularised root policy -> log-probabilities as half (B,A) (MCTS.root, boardlaw/mcts/__init__.py:142-149),
+ * prior (B,A) half = noised root logits, v (B,2) half, n_leaves (B,) i64 (boardlaw/mcts/__init__.py:151-152). */
+int bl_tree_root(const bl_tree *t, int sim, bl_half *logits, bl_half *prior, bl_half *v, int64_t *n_leaves,
+                 bl_stream stream);
+
+/* Materialises the reference's dense children (B,T,A) i16 tensor from the child lists. */
+int bl_tree_children_dense(const bl_tree *t, int16_t *children, bl_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOARDLAW_B200_H */

@@ -1,0 +1,18 @@
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run with -m gpu on the B200 box)')
+    config.addinivalue_line('markers', 'reference: needs /root/reference and the oracle/_ref build (build container only)')
+
+
+@pytest.fixture(scope='session')
+def golden_dir():
+    return ROOT / 'tests' / 'golden'
