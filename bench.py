@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""MCTS simulations/sec for vectorised Hex self-play (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--impl ours|reference]
+
+A "step" is one move of every env: ``decisions = agent(worlds)`` (n_nodes simulations per env) followed by
+``worlds.step(decisions.actions)``; value = n_envs * n_nodes * steps / time.  Prints ONE JSON line.
+For N > 1 launch under torch.distributed.run: each rank owns its own shard of envs (weak scaling) and the only
+collective is the per-move trajectory all-gather over NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# name -> (boardsize, envs per GPU, n_nodes, width, depth)
+CONFIGS = {
+    'c1': (5, 256, 16, 32, 2),
+    'c2': (9, 32768, 64, 256, 4),
+    'c3': (11, 65536, 256, 512, 8),
+    'c5-5': (5, 32768, 64, 256, 4), 'c5-7': (7, 32768, 64, 256, 4), 'c5-9': (9, 32768, 64, 256, 4),
+    'c5-11': (11, 32768, 64, 256, 4), 'c5-13': (13, 32768, 64, 256, 4),
+}
+CPU_SAMPLE_ENVS = {'c1': 256, 'c2': 512, 'c3': 64}
+
+
+def describe(config):
+    S, B, T, W, D = CONFIGS[config]
+    return f'Hex {S}x{S}, {B} envs/GPU, {T} sims/move, FCModel width {W} depth {D}'
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == 'Active' for r in self.rows)]
+        smax = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax, 'reasons': reasons, 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def make_worlds(S, B, device, seed):
+    """Hex.initial advanced by 2*A uniformly random valid moves (auto-resets spread envs over all game phases)."""
+    import torch
+    from boardlaw_b200.hex import Hex
+    g = torch.Generator(device=device).manual_seed(seed)
+    worlds = Hex.initial(B, S, device=device)
+    for _ in range(2 * S * S):
+        actions = torch.multinomial(worlds.valid.float(), 1, generator=g).squeeze(-1)
+        worlds, _ = worlds.step(actions)
+    return worlds
+
+
+def algorithmic_bytes(S, T, counters, n_desc):
+    """SURVEY.md 8(d) one-touch bytes under the reference's tensor layout, from the engine's exact counters."""
+    A, Sn = S * S, 2
+    evals, children, _, _, backup_nodes = counters[:5]
+    descend = evals * (4 * A + 5) + 4 * children          # children row 2A + logits row 2A + seat/terminal/rand, +4 per child
+    expand_step = n_desc * (6 + 2 * A + 8 + 2 * Sn + 1)
+    net_io = n_desc * (2 * A + 2 * Sn) + n_desc * 2 * A    # logits + v out, child-row init
+    backup = backup_nodes * (7 + 6 * Sn) + n_desc * T * (2 * Sn + 2)
+    return {'descend_expand': descend + expand_step, 'net': net_io, 'backup': backup}
+
+
+def net_flops(S, W, D):
+    A = S * S
+    return 2 * (2 * A * W + D * W * W + W * A + W)
+
+
+def kernel_split(agent, worlds, T, n_moves=2):
+    """Eager (un-graphed) moves with CUDA events around every C-ABI launch group: ms per move by kernel class."""
+    import torch
+    from boardlaw_b200.mcts import engine_for, dirichlet_mix
+    eng = engine_for(worlds, T)
+    net = agent.network
+    cp = net.packed()
+    acc = {'descend_expand': 0., 'net': 0., 'backup': 0., 'other': 0.}
+    launches = {'descend_expand': 0, 'net': 0, 'backup': 0}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    eng.ws.counters[:6].zero_()
+    for _ in range(n_moves):
+        pairs = []
+
+        def timed(kind, fn):
+            a, b = ev(), ev()
+            a.record(); fn(); b.record()
+            pairs.append((kind, a, b))
+        timed('other', lambda: (eng.reset(worlds.board, worlds.seats, 1 / 16), eng.eval_root(cp)))
+        timed('other', lambda: eng.set_eval(0, dirichlet_mix(eng.root_logits, worlds.valid, .25, 10), eng.root_v))
+        for sim in range(1, T):
+            timed('descend_expand', lambda: eng.descend_expand(sim))
+            timed('net', lambda: eng.eval_leaves(cp, sim))
+            timed('backup', lambda: eng.backup(sim))
+            for k in launches:
+                launches[k] += 1
+        timed('other', lambda: eng.root(T))
+        torch.cuda.synchronize()
+        for kind, a, b in pairs:
+            acc[kind] += a.elapsed_time(b)
+    counters = eng.ws.counters.cpu().tolist()
+    return {k: v / n_moves for k, v in acc.items()}, [c / n_moves for c in counters], {k: v // n_moves for k, v in launches.items()}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from boardlaw_b200 import heads
+    from boardlaw_b200.hex import Hex
+    from boardlaw_b200.mcts import MCTSAgent, engine_for
+    from boardlaw_b200.networks import FCModel, synthetic_state_dict
+    from boardlaw_b200.selfplay import SelfPlay, TrajectoryPool, record_width
+
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 under torch.distributed.run'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+
+    S, B, T, W, D = CONFIGS[args.config]
+    if args.envs:
+        B = args.envs
+    A = S * S
+    sd = synthetic_state_dict(S, W, D, seed=0)
+    net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(A), width=W, depth=D, precision=args.precision)
+    net.load_state_dict(sd)
+    net = net.to(device)
+    agent = MCTSAgent(net, n_nodes=T, c_puct=1 / 16)
+    torch.manual_seed(rank)
+    worlds = make_worlds(S, B, device, seed=rank)
+    pool = TrajectoryPool() if world > 1 else None
+    play = SelfPlay(worlds, agent, pool)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        play.step()
+    eng = engine_for(play.worlds, T)
+
+    # ---- device-resident timing -------------------------------------------------------------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = eng.launches
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            play.step()
+        if pool is not None:
+            pool.wait()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    gpu_launches = eng.launches - launches0 + args.steps      # + the env transition kernel of worlds.step
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = world * B * T * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers ---------------------------------------------------
+    hb = play.worlds.board.cpu().pin_memory()
+    hs = play.worlds.seats.cpu().pin_memory()
+    out = {'actions': torch.empty((B,), dtype=torch.int64).pin_memory(),
+           'logits': torch.empty((B, A), dtype=torch.float16).pin_memory(),
+           'v': torch.empty((B, 2), dtype=torch.float16).pin_memory(),
+           'board': torch.empty((B, S, S), dtype=torch.uint8).pin_memory(),
+           'seats': torch.empty((B,), dtype=torch.int32).pin_memory(),
+           'rewards': torch.empty((B, 2), dtype=torch.float32).pin_memory(),
+           'terminal': torch.empty((B,), dtype=torch.bool).pin_memory()}
+    h2d = hb.numel() * hb.element_size() + hs.numel() * hs.element_size()
+    d2h = sum(v.numel() * v.element_size() for v in out.values())
+
+    def e2e_step():
+        w = Hex(board=hb.to(device, non_blocking=True), seats=hs.to(device, non_blocking=True))
+        d = agent(w)
+        w2, tr = w.step(d.actions)
+        for k, src in (('actions', d.actions), ('logits', d.logits), ('v', d.v), ('board', w2.board), ('seats', w2.seats),
+                       ('rewards', tr.rewards), ('terminal', tr.terminal)):
+            out[k].copy_(src, non_blocking=True)
+        torch.cuda.current_stream().synchronize()            # the caller reads the result on the host
+        hb.copy_(out['board']); hs.copy_(out['seats'])        # next step's inputs come from the host again
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+    e2e = world * B * T * args.steps / (ms_e2e / 1e3)
+
+    # ---- per-kernel split + roofline (rank 0) -------------------------------------------------------------------
+    result = None
+    if rank == 0:
+        split, counters, per_move_launches = kernel_split(agent, play.worlds, T)
+        peaks = {}
+        pk = ROOT / 'MEASURED_PEAKS.json'
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm_peak, hbm_src = (peaks['hbm_gbs'], 'measured') if 'hbm_gbs' in peaks else (6650., 'fallback')
+        tc_peak = peaks.get('bf16_tflops_sustained', 1400.)
+        n_desc = B * (T - 1)
+        bytes_by = algorithmic_bytes(S, T, counters, n_desc)
+        dominant = max(('descend_expand', 'net', 'backup'), key=lambda k: split[k])
+        if dominant == 'net':
+            flops = net_flops(S, W, D) * n_desc
+            achieved = flops / (split['net'] / 1e3) / 1e12
+            roofline = {'kernel': 'fc_forward (leaf evaluation)', 'bound': 'tensor', 'achieved': achieved, 'peak': tc_peak,
+                        'unit': 'TFLOP/s', 'frac': achieved / tc_peak, 'traffic': None,
+                        'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback'}
+        else:
+            achieved = bytes_by[dominant] / (split[dominant] / 1e3) / 1e9
+            roofline = {'kernel': dominant, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                        'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': hbm_src}
+        roofline['ms_per_move_by_kernel'] = {k: round(v, 3) for k, v in split.items()}
+        roofline['launches_per_move_by_kernel'] = per_move_launches
+        roofline['algorithmic_bytes_per_move'] = {k: int(v) for k, v in bytes_by.items()}
+        roofline['net_tflops'] = net_flops(S, W, D) * n_desc / (split['net'] / 1e3) / 1e12
+        roofline['tree_shape'] = {'policy_evals_per_descent': counters[0] / max(counters[3], 1),
+                                  'children_per_eval': counters[1] / max(counters[0], 1),
+                                  'newton_iters_per_eval': counters[2] / max(counters[0], 1)}
+
+        cpu = cpu_baseline(args.config, sd, steps=3, warmup=1) if (world == 1 and not args.no_cpu) else None
+        result = {
+            'metric': 'MCTS sims/sec', 'value': value, 'unit': 'sims/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'f16',
+            'data': 'synthetic (random-playout positions, random-init FCModel weights with alpha~U(.1,.5))',
+            'config': {'workload': f'{args.config}: {describe(args.config)}', 'envs_per_gpu': B, 'global_envs': B * world,
+                       'n_nodes': T, 'boardsize': S, 'width': W, 'depth': D, 'net_precision': args.precision,
+                       'parallelism': f'env-sharded x{world}' + (', per-move NCCL all-gather of trajectory records' if world > 1 else ''),
+                       'l2_policy': 'tree workspace per GPU exceeds L2 (inputs larger than L2), no flush'
+                       if B * T * (4 * A + 2 * A) > 126e6 else 'working set fits L2; not flushed'},
+            'e2e': {'value': e2e, 'unit': 'sims/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(gpu_launches),
+            'clocks': clocks.summary(),
+            'roofline': roofline,
+            'cpu_baseline': cpu,
+        }
+        if world > 1:
+            result['config']['allgather_bytes_per_rank_per_move'] = B * record_width(A)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if result is not None:
+        print(json.dumps(result))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU implementation of the path (oracle/_ref kernels when built, else the C port)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_baseline(config, sd, steps, warmup):
+    import torch
+    from oracle import build_ref, pyref
+    S, B, T, W, D = CONFIGS[config]
+    Bc = min(CPU_SAMPLE_ENVS.get(config, 512 if S <= 9 else 128), B)
+    if build_ref.available('O0'):
+        ops, kind = pyref.RefOps('O0'), 'reference'
+    else:
+        ops, kind = pyref.COps(), 'port'
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(0)
+    w = pyref.HexWorld.initial(Bc, S, ops)
+    for _ in range(2 * S * S):
+        w, _ = w.step(torch.multinomial(w.valid.float(), 1, generator=g).squeeze(-1))
+    net = pyref.FCNet(sd)
+
+    def move(w):
+        d = pyref.agent_call(w, net, n_nodes=T, c_puct=1 / 16)
+        w2, _ = w.step(d.actions)
+        return w2
+    for _ in range(warmup):
+        w = move(w)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w = move(w)
+    dt = time.perf_counter() - t0
+    return {'value': Bc * T * steps / dt, 'unit': 'sims/s', 'cores': torch.get_num_threads(), 'kind': kind,
+            'host_cpus': os.cpu_count(), 'seconds': dt,
+            'sample': f'{steps} moves of {Bc} envs (of {B}) at {describe(config)}; '
+                      + ('reference CPU kernels built from its unmodified sources at the reference loader\'s flags (-O0), '
+                         'single-threaded per-env loops as in the reference, torch ops on all threads; Python orchestration restated (oracle/pyref.py)'
+                         if kind == 'reference' else 'C restatement of the reference kernels (oracle/boardlaw_oracle.c, -O2)')}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    import torch
+    from boardlaw_b200.networks import synthetic_state_dict
+    S, B, T, W, D = CONFIGS[args.config]
+    sd = synthetic_state_dict(S, W, D, seed=0)
+    t0 = time.perf_counter()
+    cpu = cpu_baseline(args.config, sd, steps=args.steps, warmup=min(args.warmup, 1))
+    Bc = CPU_SAMPLE_ENVS.get(args.config, 512)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'MCTS sims/sec', 'value': cpu['value'], 'unit': 'sims/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': cpu['seconds'] / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{args.config}: {describe(args.config)}', 'sample_envs': min(Bc, B), 'device': 'host CPU'},
+        'cpu_baseline': {k: cpu[k] for k in ('kind', 'cores', 'sample', 'value', 'unit', 'host_cpus')},
+        'e2e': {'value': cpu['value'], 'unit': 'sims/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'amp'])
+    ap.add_argument('--envs', type=int, default=0, help='override envs per GPU (debugging)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

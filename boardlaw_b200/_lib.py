@@ -31,7 +31,7 @@ class Tree(Structure):
                 ('terminal', c_void_p), ('parents', c_void_p), ('relation', c_void_p),
                 ('first_child', c_void_p), ('next_sib', c_void_p), ('n', c_void_p), ('w', c_void_p),
                 ('v', c_void_p), ('rewards', c_void_p), ('c_puct', c_void_p), ('leaf', c_void_p),
-                ('leaf_parent', c_void_p), ('leaf_action', c_void_p), ('qrange', c_void_p),
+                ('leaf_parent', c_void_p), ('leaf_action', c_void_p), ('prior', c_void_p), ('qrange', c_void_p),
                 ('counters', c_void_p), ('exp_lut', c_void_p)]
 
 
@@ -52,6 +52,15 @@ SIGNATURES = {
     'bl_mcts_transition_q': (c_int, [P] * 4 + [c_int] * 3 + [P]),
     'bl_fc_scratch_bytes': (c_int64, [POINTER(FCParams), c_int]),
     'bl_fc_forward': (c_int, [POINTER(FCParams), P, P, P, P, P, c_int, P]),
+    'bl_tree_reset': (c_int, [POINTER(Tree), P, P, c_float, P]),
+    'bl_tree_set_eval': (c_int, [POINTER(Tree), c_int, P, P, c_int, P]),
+    'bl_tree_descend_expand': (c_int, [POINTER(Tree), c_int, P, c_uint64, P]),
+    'bl_tree_backup': (c_int, [POINTER(Tree), c_int, P]),
+    'bl_tree_eval_scratch_bytes': (c_int64, [POINTER(Tree), POINTER(FCParams)]),
+    'bl_tree_eval_leaves': (c_int, [POINTER(Tree), POINTER(FCParams), c_int, P, P]),
+    'bl_tree_eval_root': (c_int, [POINTER(Tree), POINTER(FCParams), P, P, P, P]),
+    'bl_tree_root': (c_int, [POINTER(Tree), c_int, P, P, P, P, P]),
+    'bl_tree_children_dense': (c_int, [POINTER(Tree), P, P]),
 }
 
 _lib = None
@@ -143,3 +152,16 @@ def exp_lut(device):
     if key not in _exp_dev:
         _exp_dev[key] = torch.from_numpy(exp_table_host()).to(device)
     return _exp_dev[key]
+
+
+_log_dev = {}
+
+
+def log_lut(device):
+    """Device copy of ``h.float().log().half()`` over every binary16 pattern, evaluated by torch on the host exactly
+    as ``MCTS.root`` does on the reference's CPU path (boardlaw/mcts/__init__.py:147)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _log_dev:
+        every = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(torch.float16)
+        _log_dev[key] = every.float().log().half().to(device)
+    return _log_dev[key]

@@ -1,0 +1,202 @@
+"""The fused search engine: a persistent, privately laid out tree workspace driven through the ``bl_tree_*``
+entry points of libboardlaw_b200.so (include/boardlaw_b200.h), replacing the per-move allocation and the
+~120 kernel launches + host syncs per simulation of ``MCTS.simulate`` (boardlaw/mcts/__init__.py:108-140).
+
+One ``SearchEngine`` owns the workspace for a fixed (n_envs, boardsize, n_nodes) on one device; the per-move
+work is three launches per simulation (descend+expand+step, network, backup+q-range), captured in a CUDA
+graph after the first move.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, arrdict
+from ._lib import ptr, check
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class SearchEngine:
+
+    def __init__(self, n_envs, boardsize, n_nodes, device, mirror_logits=False, seed=0):
+        self.B, self.S, self.T = n_envs, boardsize, n_nodes
+        self.A, self.Sn = boardsize * boardsize, 2
+        self.AP, self.BP = _round_up(self.A, 4), _round_up(self.A, 16)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('SearchEngine runs on a CUDA device only (there is no CPU path)')
+        self.seed = seed
+        B, T, A, Sn, dev = self.B, self.T, self.A, self.Sn, self.device
+        z = lambda shape, dtype: torch.zeros(shape, dtype=dtype, device=dev)
+        self.ws = arrdict.arrdict(
+            pi=z((B, T, self.AP), torch.float32),
+            board=z((B, T, self.BP), torch.uint8),
+            seats=z((B, T), torch.uint8),
+            terminal=z((B, T), torch.uint8),
+            parents=z((B, T), torch.int16), relation=z((B, T), torch.int16),
+            first_child=z((B, T), torch.int16), next_sib=z((B, T), torch.int16),
+            n=z((B, T), torch.int16), w=z((B, T, Sn), torch.float16), v=z((B, T, Sn), torch.float16),
+            rewards=z((B, T, Sn), torch.float16), c_puct=z((B,), torch.float16),
+            leaf=z((B,), torch.int16), leaf_parent=z((B,), torch.int16), leaf_action=z((B,), torch.int16),
+            prior=z((B, A), torch.float16), qrange=z((T + 1, 2), torch.float32), counters=z((8,), torch.int64))
+        if mirror_logits:
+            self.ws['logits'] = torch.full((B, T, A), np.nan, dtype=torch.float16, device=dev)
+        self.exp_lut = _lib.exp_lut(dev)
+        self.log_lut = _lib.log_lut(dev)
+        fields = {k: self.ws[k].data_ptr() for k in self.ws}
+        fields.setdefault('logits', None)
+        self.ctree = _lib.Tree(B=B, T=T, S=self.S, A=A, Sn=Sn, AP=self.AP, BP=self.BP, exp_lut=self.exp_lut.data_ptr(), **fields)
+        self._tp = ctypes.byref(self.ctree)
+        # static I/O buffers (graph-replay safe)
+        self.in_board = z((B, self.S, self.S), torch.uint8)
+        self.in_seats = z((B,), torch.int32)
+        self.root_logits = z((B, A), torch.float32)
+        self.root_v = z((B, 2), torch.float32)
+        self.out_logits = z((B, A), torch.float16)
+        self.out_v = z((B, 2), torch.float16)
+        self.out_n_leaves = z((B,), torch.int64)
+        self._scratch = None
+        self._scratch_key = None
+        self._graphs = {}
+        self.sim = 0
+        self.move = 0
+        self.launches = 0          # kernels of libboardlaw_b200.so launched (or replayed from a graph) so far
+        self._graph_launches = {}
+
+    # ---- thin wrappers over the C ABI ------------------------------------------------------------------
+    def _stream(self):
+        return _lib.stream_for(self.device)
+
+    def reset(self, board, seats, c_puct):
+        self.in_board.copy_(board)
+        self.in_seats.copy_(seats)
+        self._reset(c_puct)
+
+    def _reset(self, c_puct):
+        check(_lib.lib().bl_tree_reset(self._tp, ptr(self.in_board), ptr(self.in_seats), float(c_puct), self._stream()),
+              'bl_tree_reset')
+        self.sim = 0
+        self.launches += 1
+
+    def scratch_for(self, cparams):
+        key = (cparams.W, cparams.D)
+        if self._scratch_key != key:
+            n = _lib.lib().bl_tree_eval_scratch_bytes(self._tp, ctypes.byref(cparams))
+            self._scratch = torch.empty((max(int(n), 1),), dtype=torch.uint8, device=self.device)
+            self._scratch_key = key
+        return self._scratch
+
+    def eval_root(self, cparams):
+        check(_lib.lib().bl_tree_eval_root(self._tp, ctypes.byref(cparams), ptr(self.root_logits), ptr(self.root_v),
+                                           ptr(self.scratch_for(cparams)), self._stream()), 'bl_tree_eval_root')
+        self.launches += cparams.D + 4         # gather + intake + D residuals + policy + heads
+        return self.root_logits, self.root_v
+
+    def set_eval(self, node, logits, v):
+        half = logits.dtype == torch.float16
+        assert logits.dtype in (torch.float16, torch.float32) and v.dtype == logits.dtype
+        assert logits.shape == (self.B, self.A) and v.shape == (self.B, 2)
+        logits, v = logits.contiguous(), v.contiguous()
+        check(_lib.lib().bl_tree_set_eval(self._tp, node, ptr(logits), ptr(v), int(half), self._stream()), 'bl_tree_set_eval')
+        self.launches += 1
+        if node == 0:
+            self.sim = 1
+
+    def descend_expand(self, sim, rands=None):
+        if rands is not None:
+            rands = _lib.proxy(rands.contiguous(), torch.float16, 2, 'rands')
+            assert rands.shape == (self.B, self.T)
+        check(_lib.lib().bl_tree_descend_expand(self._tp, sim, ptr(rands), self.seed, self._stream()), 'bl_tree_descend_expand')
+        self.launches += 1
+
+    def eval_leaves(self, cparams, sim):
+        check(_lib.lib().bl_tree_eval_leaves(self._tp, ctypes.byref(cparams), sim, ptr(self.scratch_for(cparams)),
+                                             self._stream()), 'bl_tree_eval_leaves')
+        self.launches += cparams.D + 5         # gather + network (D+3) + set_eval
+
+    def backup(self, sim):
+        check(_lib.lib().bl_tree_backup(self._tp, sim, self._stream()), 'bl_tree_backup')
+        self.launches += 1
+        self.sim = sim + 1
+
+    def root(self, sim=None):
+        sim = self.sim if sim is None else sim
+        check(_lib.lib().bl_tree_root(self._tp, sim, ptr(self.log_lut), ptr(self.out_logits), ptr(self.out_v),
+                                      ptr(self.out_n_leaves), self._stream()), 'bl_tree_root')
+        self.launches += 1
+        return self.out_logits, self.out_v, self.out_n_leaves
+
+    def children_dense(self):
+        out = torch.empty((self.B, self.T, self.A), dtype=torch.int16, device=self.device)
+        check(_lib.lib().bl_tree_children_dense(self._tp, ptr(out), self._stream()), 'bl_tree_children_dense')
+        return out
+
+    def leaf_worlds(self):
+        """(board (B,S,S) u8, seats (B,) i32) of the current leaves — what the network is evaluated on."""
+        idx = self.ws.leaf.long().clamp(min=0)
+        envs = torch.arange(self.B, device=self.device)
+        board = self.ws.board[envs, idx][:, :self.A].reshape(self.B, self.S, self.S).contiguous()
+        return board, self.ws.seats[envs, idx].int()
+
+    # ---- whole searches -------------------------------------------------------------------------------------
+    def _simulate_all(self, cparams, first, last):
+        for sim in range(first, last):
+            self.descend_expand(sim)
+            self.eval_leaves(cparams, sim)
+            self.backup(sim)
+        self.root(last)
+
+    def search(self, board, seats, network, c_puct=1 / 16, noise_eps=.25, alpha_scale=10, noise=None, use_graph=True):
+        """One whole search (MCTS.__init__ + initialize + (n_nodes-1) x simulate + root).  Returns
+        (logits half (B,A), prior half (B,A), v half (B,2), n_leaves i64 (B,)) as views of static buffers."""
+        from .mcts import dirichlet_mix
+        cparams = network.packed()
+        self.in_board.copy_(board)
+        self.in_seats.copy_(seats)
+        self.ws.counters[6:7].fill_(self.move)       # keys the in-kernel random stream of this move
+        self.move += 1
+        key = (cparams.W, cparams.D, cparams.precision, float(c_puct), id(network), network._pack_key)
+        if not use_graph:
+            self._reset(c_puct)
+            self.eval_root(cparams)
+        else:
+            g = self._graphs.get(('head',) + key)
+            if g is None:
+                self._reset(c_puct); self.eval_root(cparams)            # warm-up: sets kernel attributes, allocs
+                g = torch.cuda.CUDAGraph()
+                before = self.launches
+                with torch.cuda.graph(g):
+                    self._reset(c_puct)
+                    self.eval_root(cparams)
+                self._graph_launches[('head',) + key] = self.launches - before
+                self.launches = before                                   # captured, not launched
+                self._graphs[('head',) + key] = g
+            g.replay()
+            self.launches += self._graph_launches[('head',) + key]
+        valid = self.in_board.reshape(self.B, self.A) == 0
+        valid = torch.where(self.in_seats[:, None] == 1,
+                            (self.in_board.transpose(1, 2).reshape(self.B, self.A) == 0), valid)
+        mixed = dirichlet_mix(self.root_logits, valid, noise_eps, alpha_scale, noise)
+        self.set_eval(0, mixed, self.root_v)
+        if not use_graph:
+            self._simulate_all(cparams, 1, self.T)
+        else:
+            g = self._graphs.get(('sims',) + key)
+            if g is None:
+                self._simulate_all(cparams, 1, self.T)                       # warm-up on this very tree (discarded)
+                # re-establish the state the graph expects, then capture
+                self._reset(c_puct); self.eval_root(cparams); self.set_eval(0, mixed, self.root_v)
+                g = torch.cuda.CUDAGraph()
+                before = self.launches
+                with torch.cuda.graph(g):
+                    self._simulate_all(cparams, 1, self.T)
+                self._graph_launches[('sims',) + key] = self.launches - before
+                self.launches = before
+                self._graphs[('sims',) + key] = g
+            g.replay()
+            self.launches += self._graph_launches[('sims',) + key]
+        self.sim = self.T
+        return self.out_logits, self.ws.prior, self.out_v, self.out_n_leaves

@@ -27,6 +27,19 @@ def dirichlet_noise(logits, valid, eps, alpha_scale=10):
     return (logits.exp() * (1 - eps) + draw * eps).log()
 
 
+def dirichlet_mix(logits, valid, eps, alpha_scale=10, draw=None):
+    """``dirichlet_noise`` with the Dirichlet draw optionally injected (``draw`` (B,A) f32, the raw sample before
+    masking) so that seeded runs can be compared across devices."""
+    if draw is None:
+        conc = torch.full((valid.shape[-1],), alpha_scale / logits.size(-1), dtype=torch.float, device=logits.device)
+        draw = torch.distributions.Dirichlet(conc).sample(logits.shape[:-1])
+    else:
+        draw = draw.to(logits.device, torch.float).clone()
+    draw[~valid] = 0.
+    draw = draw / draw.sum(-1, keepdims=True)
+    return (logits.exp() * (1 - eps) + draw * eps).log()
+
+
 class MCTS:
 
     def __init__(self, world, n_nodes=64, c_puct=1 / 16, noise_eps=.25, alpha_scale=10):
@@ -59,11 +72,11 @@ class MCTS:
         self.noise_eps = noise_eps
         self.alpha_scale = alpha_scale
 
-    def initialize(self, network):
+    def initialize(self, network, noise=None):
         world = self.worlds[:, 0]
         with torch.no_grad():
             decisions = network(world)
-        self.decisions.logits[:, self.sim] = dirichlet_noise(decisions.logits, world.valid, self.noise_eps, self.alpha_scale)
+        self.decisions.logits[:, self.sim] = dirichlet_mix(decisions.logits, world.valid, self.noise_eps, self.alpha_scale, noise)
         self.decisions.v[:, 0] = decisions.v
         self.sim += 1
 
@@ -117,8 +130,68 @@ class MCTS:
         return ((self.tree.children == -1).all(-1) & (self.tree.parents != -1)).sum(-1)
 
 
-def mcts(worlds, network, **kwargs):
-    m = MCTS(worlds, **kwargs)
+class EngineSearch:
+    """What ``mcts()`` returns on the fused path: the ``root()`` / ``n_leaves()`` / ``sim`` / ``envs`` members
+    ``MCTSAgent`` uses, plus the reference's tree tensors materialised on demand from the engine workspace."""
+
+    def __init__(self, eng, outputs):
+        self.engine = eng
+        self.device = eng.device
+        self.n_envs, self.n_nodes, self.n_seats, self.n_actions = eng.B, eng.T, eng.Sn, eng.A
+        self.envs = torch.arange(eng.B, device=eng.device)
+        self.sim = eng.T
+        self._out = outputs
+
+    def root(self):
+        logits, prior, v, _ = self._out
+        return arrdict.arrdict(logits=logits, prior=prior, v=v)
+
+    def n_leaves(self):
+        return self._out[3]
+
+    @property
+    def tree(self):
+        ws = self.engine.ws
+        return arrdict.arrdict(children=self.engine.children_dense(), parents=ws.parents, relation=ws.relation)
+
+    @property
+    def stats(self):
+        return arrdict.arrdict(n=self.engine.ws.n, w=self.engine.ws.w)
+
+    @property
+    def transitions(self):
+        return arrdict.arrdict(rewards=self.engine.ws.rewards, terminal=self.engine.ws.terminal.bool())
+
+
+_engines = {}
+
+
+def engine_for(world, n_nodes):
+    """Workspaces are persistent: one per (device, n_envs, boardsize, n_nodes), reused move after move."""
+    from ..engine import SearchEngine
+    key = (str(world.device), world.n_envs, world.boardsize, n_nodes)
+    if key not in _engines:
+        if len(_engines) >= 4:                       # arena-style callers vary n_envs per call: bound the cache
+            _engines.pop(next(iter(_engines)))
+        _engines[key] = SearchEngine(world.n_envs, world.boardsize, n_nodes, world.device)
+    return _engines[key]
+
+
+def _fusable(worlds, network):
+    from ..hex import Hex
+    from ..networks import FCModel
+    return isinstance(worlds, Hex) and isinstance(network, FCModel) and worlds.board.ndim == 3 and worlds.device.type == 'cuda'
+
+
+def mcts(worlds, network, n_nodes=64, c_puct=1 / 16, noise_eps=.25, alpha_scale=10, fused=None, **kwargs):
+    """boardlaw/mcts/__init__.py:200-207.  Hex worlds with an FCModel run on the fused engine; anything else (toy
+    worlds, arbitrary network callables) runs the op-level ``MCTS`` loop."""
+    fused = _fusable(worlds, network) if fused is None else fused
+    if fused and n_nodes > 1:
+        eng = engine_for(worlds, n_nodes)
+        out = eng.search(worlds.board, worlds.seats, network, c_puct=c_puct, noise_eps=noise_eps, alpha_scale=alpha_scale, **kwargs)
+        return EngineSearch(eng, out)
+    m = MCTS(worlds, n_nodes=n_nodes, c_puct=c_puct, noise_eps=noise_eps, alpha_scale=alpha_scale)
     m.initialize(network)
     for _ in range(m.n_nodes - 1):
         m.simulate(network)

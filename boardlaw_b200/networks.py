@@ -108,3 +108,25 @@ class FCModel(nn.Module):
         with torch.no_grad():
             logits, v = self.evaluate(worlds.board, worlds.seats)
         return arrdict.arrdict(logits=logits, v=v)
+
+
+def synthetic_state_dict(boardsize, width, depth, seed=0):
+    """Random-init FCModel weights for benchmarks (no checkpoints exist offline): torch-default-style uniform fan-in
+    init for the plain layers, gaussian sqrt(2/W) residual weights, and α ~ U(0.1, 0.5) in every ReZero block —
+    at the reference's own init α = 0 (boardlaw/networks.py:15) the residual weights would not contribute at all."""
+    g = torch.Generator().manual_seed(seed)
+    A = boardsize * boardsize
+
+    def lin(o, i):
+        bound = 1 / i ** .5
+        return ((torch.rand((o, i), generator=g) * 2 - 1) * bound, (torch.rand((o,), generator=g) * 2 - 1) * bound)
+
+    sd = {}
+    sd['body.0.weight'], sd['body.0.bias'] = lin(width, 2 * A)
+    for k in range(1, depth + 1):
+        sd[f'body.{k}.weight'] = torch.randn((width, width), generator=g) * (2 / width) ** .5
+        sd[f'body.{k}.bias'] = (torch.rand((width,), generator=g) * 2 - 1) / width ** .5
+        sd[f'body.{k}.α'] = torch.rand((), generator=g) * .4 + .1
+    sd['policy.core.weight'], sd['policy.core.bias'] = lin(A, width)
+    sd['value.core.weight'], sd['value.core.bias'] = lin(1, width)
+    return sd

@@ -164,44 +164,51 @@ typedef struct bl_tree {
     int16_t *leaf;        /* (B,)   i16 leaf of the current simulation                              */
     int16_t *leaf_parent; /* (B,)   i16                                                             */
     int16_t *leaf_action; /* (B,)   i16                                                             */
+    bl_half *prior;       /* (B,A)  half: the (noised) root logits as stored, = decisions.logits[:,0]       */
     float *qrange;        /* (T+1,2) per-simulation (min,max) of w/(n+1e-4), ordered-int encoded    */
     uint64_t *counters;   /* (8,) policy evals, children seen, newton iters, descents, backup nodes */
     const float *exp_lut; /* (65536,)                                                               */
 } bl_tree;
 
-/* Resets the workspace for a new search rooted at (board (B,S,S) u8, seats (B,) i32). */
+/* Resets the workspace for a new search rooted at (board (B,S,S) u8, seats (B,) i32).  The in-kernel random
+ * stream is keyed by (seed, counters[6]); the host stores the move index in counters[6] before each search. */
 int bl_tree_reset(const bl_tree *t, const uint8_t *board, const int32_t *seats, float c_puct,
                   bl_stream stream);
 
-/* Writes the network evaluation of node `node` for every env: logits (B,A) f32 (or half if
- * logits_are_half) and v (B,2), rounded to half exactly as `decisions.half()` does
- * (boardlaw/mcts/__init__.py:135-136), stored as pi = exp_lut[half(logit)].
- * node < 0 means "the current leaf of each env" (t->leaf). */
+/* Writes the network evaluation of node `node` for every env: logits (B,A) and v (B,2), f32 or half
+ * (inputs_are_half), rounded to half exactly as `decisions.half()` does (boardlaw/mcts/__init__.py:135-136)
+ * and stored as pi = exp_lut[half(logit)].  node < 0 means "the current leaf of each env" (t->leaf). */
 int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, const void *v,
                      int inputs_are_half, bl_stream stream);
 
-/* descend + expand + env step of simulation `sim` (boardlaw/mcts/__init__.py:108-129):
- * writes t->leaf / leaf_parent / leaf_action, links new nodes, steps the parent's board into the
- * leaf slot, records rewards / terminal.  rands: (B,T) half injected random numbers, or NULL to
- * draw them in-kernel from Philox4x32-10 keyed by (seed, stream_id) and counted by (env, node). */
+/* descend + expand + env step of simulation `sim` (boardlaw/mcts/__init__.py:108-129): writes
+ * t->leaf / leaf_parent / leaf_action, links new nodes, steps the parent's board into the leaf slot, records
+ * rewards / terminal.  rands: (B,T) half injected random numbers (indexed by node, as cuda.cu:158), or NULL to
+ * draw them in-kernel from Philox4x32-10 keyed by (seed, move counter) and counted by (env, sim, node). */
 int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed,
-                           uint64_t stream_id, bl_stream stream);
+                           bl_stream stream);
 
 /* backup of the current leaves (boardlaw/mcts/cpp/cuda.cu:205-248) + the q-range scan used by the next
  * descent (transition_q's global min/max, cuda.cu:101-105), stored in qrange[sim+1]. */
 int bl_tree_backup(const bl_tree *t, int sim, bl_stream stream);
 
-/* Network evaluation of the current leaves straight into the tree (fused set_eval). */
-int bl_tree_eval_leaves(const bl_tree *t, const bl_fc_params *p, int sim, bl_stream stream);
+/* Device scratch needed by bl_tree_eval_leaves / bl_tree_eval_root. */
+int64_t bl_tree_eval_scratch_bytes(const bl_tree *t, const bl_fc_params *p);
+
+/* Network evaluation of the current leaves straight into the tree. */
+int bl_tree_eval_leaves(const bl_tree *t, const bl_fc_params *p, int sim, void *scratch, bl_stream stream);
 
 /* Root evaluation: logits f32 (B,A) and v f32 (B,2) of node 0 are returned to the caller, who mixes the
  * Dirichlet noise (boardlaw/mcts/__init__.py:13-24) and hands the result to bl_tree_set_eval(node=0). */
-int bl_tree_eval_root(const bl_tree *t, const bl_fc_params *p, float *logits, float *v, bl_stream stream);
+int bl_tree_eval_root(const bl_tree *t, const bl_fc_params *p, float *logits, float *v, void *scratch,
+                      bl_stream stream);
 
 /* Regularised root policy -> log-probabilities as half (B,A) (MCTS.root, boardlaw/mcts/__init__.py:142-149),
- * prior (B,A) half = noised root logits, v (B,2) half, n_leaves (B,) i64 (boardlaw/mcts/__init__.py:151-152). */
-int bl_tree_root(const bl_tree *t, int sim, bl_half *logits, bl_half *prior, bl_half *v, int64_t *n_leaves,
-                 bl_stream stream);
+ * v (B,2) half, n_leaves (B,) i64 (boardlaw/mcts/__init__.py:151-152).  `sim` = number of nodes evaluated so far.
+ * log_lut[h] (65536 halves, device) = half(log(float(h))) as the caller's framework evaluates
+ * `r.float().log().half()` (boardlaw/mcts/__init__.py:147). */
+int bl_tree_root(const bl_tree *t, int sim, const bl_half *log_lut, bl_half *logits, bl_half *v,
+                 int64_t *n_leaves, bl_stream stream);
 
 /* Materialises the reference's dense children (B,T,A) i16 tensor from the child lists. */
 int bl_tree_children_dense(const bl_tree *t, int16_t *children, bl_stream stream);
