@@ -181,9 +181,9 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
     if (ok) {
         const int seat = t.seats[node0 + parent];
         int win = bl_hex_place<uint8_t>(sm.bd + tid, sm.stk + tid, BPITCH, t.S, seat, action);
-        float r0 = win == 1 ? 1.f : (win == 2 ? -1.f : 0.f);
+        float r0 = win == 1 ? 1.f : (win == 2 ? -1.f : 0.f), r1 = win == 1 ? -1.f : (win == 2 ? 1.f : 0.f);
         t.rewards[(node0 + leaf) * Sn + 0] = bl_f2h(r0);
-        t.rewards[(node0 + leaf) * Sn + 1] = bl_f2h(-r0);
+        t.rewards[(node0 + leaf) * Sn + 1] = bl_f2h(r1);
         t.terminal[node0 + leaf] = win != 0;
         t.seats[node0 + leaf] = win ? 0 : (uint8_t)(1 - seat);
         if (win)

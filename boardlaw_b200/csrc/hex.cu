@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(NT) hex_step_kernel(
         }
         if (ok) win = bl_hex_place<StkT>(sb + tid, stk + tid, PITCH, S, seat, (int)action);
 
-        float r0 = win == 1 ? 1.f : (win == 2 ? -1.f : 0.f);
-        reinterpret_cast<float2 *>(rewards)[b] = make_float2(r0, -r0);
+        float r0 = win == 1 ? 1.f : (win == 2 ? -1.f : 0.f), r1 = win == 1 ? -1.f : (win == 2 ? 1.f : 0.f);
+        reinterpret_cast<float2 *>(rewards)[b] = make_float2(r0, r1);
         if (MODE & F_TRANSITION) {
             bool term = reset && win != 0;                        // hex/__init__.py:183
             terminal[b] = term ? 1 : 0;

@@ -121,8 +121,11 @@ class MCTS:
 
     def root(self):
         r = cuda.root(self._cuda())
+        # log of the half probabilities through the host-evaluated table: identical to the reference's CPU path
+        # `r.float().log().half()` (boardlaw/mcts/__init__.py:147) for every input, on any device
+        from .. import _lib
         return arrdict.arrdict(
-            logits=r.float().log().half(),
+            logits=_lib.log_lut(r.device)[r.view(torch.int16).long() & 0xFFFF],
             prior=self.decisions.logits[:, 0],
             v=self.decisions.v[:, 0])
 
