@@ -21,7 +21,7 @@ class FCParams(Structure):
     _fields_ = [('S', c_int), ('W', c_int), ('D', c_int), ('precision', c_int),
                 ('w_in', c_void_p), ('b_in', c_void_p), ('w_res', c_void_p), ('b_res', c_void_p),
                 ('alpha', c_void_p), ('w_pol', c_void_p), ('b_pol', c_void_p), ('w_val', c_void_p),
-                ('b_val', c_void_p), ('packed', c_void_p)]
+                ('b_val', c_void_p), ('packed', c_void_p), ('b_head', c_void_p)]
 
 
 class Tree(Structure):
@@ -32,7 +32,7 @@ class Tree(Structure):
                 ('first_child', c_void_p), ('next_sib', c_void_p), ('n', c_void_p), ('w', c_void_p),
                 ('v', c_void_p), ('rewards', c_void_p), ('c_puct', c_void_p), ('leaf', c_void_p),
                 ('leaf_parent', c_void_p), ('leaf_action', c_void_p), ('prior', c_void_p), ('qrange', c_void_p),
-                ('counters', c_void_p), ('exp_lut', c_void_p)]
+                ('counters', c_void_p), ('exp_lut', c_void_p), ('scratch', c_void_p), ('scratch_bytes', c_int64)]
 
 
 P = c_void_p
@@ -56,6 +56,8 @@ SIGNATURES = {
     'bl_tree_set_eval': (c_int, [POINTER(Tree), c_int, P, P, c_int, P]),
     'bl_tree_descend_expand': (c_int, [POINTER(Tree), c_int, P, c_uint64, P]),
     'bl_tree_backup': (c_int, [POINTER(Tree), c_int, P]),
+    'bl_debug_set_descend_variant': (c_int, [c_int]),
+    'bl_selftest_division': (c_int, [c_uint64, c_int, c_int, P, P]),
     'bl_tree_eval_scratch_bytes': (c_int64, [POINTER(Tree), POINTER(FCParams)]),
     'bl_tree_eval_leaves': (c_int, [POINTER(Tree), POINTER(FCParams), c_int, P, P]),
     'bl_tree_eval_root': (c_int, [POINTER(Tree), POINTER(FCParams), P, P, P, P]),

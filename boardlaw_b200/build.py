@@ -25,7 +25,9 @@ SOURCES = {
     'hex.cu': [],
     'mcts.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
     'engine.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
+    'descend.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
     'net.cu': [],
+    'net_tc.cu': [],
     'host.cu': [],
 }
 

@@ -12,6 +12,7 @@
 // warp-cooperative coalesced row loads into lane-major shared-memory columns (odd pitch => conflict-free both ways).
 //
 // Compiled with -fmad=false -prec-div=true -ftz=false (see build.py).
+#include "engine_internal.cuh"
 #include "hex_core.cuh"
 #include "mcts_core.cuh"
 
@@ -22,7 +23,7 @@ constexpr int FP = ENT + 1;        // float column pitch (odd: conflict-free for
 constexpr int BPITCH = ENT + 4;    // byte column pitch (17 words: consecutive cells land on distinct banks)
 
 // counters slots
-enum { C_EVALS = 0, C_CHILDREN = 1, C_ITERS = 2, C_DESCENTS = 3, C_BACKUP_NODES = 4, C_ERRORS = 5, C_MOVE = 6 };
+int g_descend_variant = 2;
 
 __global__ void __launch_bounds__(256) reset_kernel(bl_tree t, const uint8_t *__restrict__ board,
                                                     const int32_t *__restrict__ seats, bl_half c_puct) {
@@ -356,6 +357,7 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (sim < 1 || sim >= t->T) return -1;
+    if (g_descend_variant == 2) return bl_descend_v2(t, sim, rands, seed, bl_cu(stream));
     size_t smem = descend_smem(t->A);
     if (smem > 227 * 1024) return -2;
     if (smem > 48 * 1024) {
@@ -364,6 +366,12 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
     }
     descend_expand_kernel<<<(t->B + ENT - 1) / ENT, ENT, smem, bl_cu(stream)>>>(*t, sim, rands, seed);
     BL_LAUNCH_CHECK();
+}
+
+extern "C" int bl_debug_set_descend_variant(int variant) {
+    if (variant != 1 && variant != 2) return -1;
+    g_descend_variant = variant;
+    return 0;
 }
 
 extern "C" int bl_tree_backup(const bl_tree *t, int sim, bl_stream stream) {

@@ -136,6 +136,11 @@ __global__ void __launch_bounds__(256) heads_kernel(
 
 }  // namespace
 
+// net_tc.cu
+int bl_fc_forward_tc(const bl_fc_params *p, const uint8_t *board, long long board_pitch, const int32_t *seats, float *logits,
+                     float *v, int B, cudaStream_t st);
+bool bl_fc_tc_supported(const bl_fc_params *p);
+
 extern "C" int64_t bl_fc_scratch_bytes(const bl_fc_params *p, int B) {
     return (int64_t)sizeof(float) * B * (2 * (int64_t)p->W + (int64_t)p->S * p->S);
 }
@@ -147,6 +152,7 @@ extern "C" int bl_fc_forward(const bl_fc_params *p, const uint8_t *board, const 
     if (B == 0) return 0;
     cudaStream_t st = bl_cu(stream);
     const int S = p->S, A = S * S, W = p->W;
+    if (bl_fc_tc_supported(p)) return bl_fc_forward_tc(p, board, (long long)A, seats, logits, v, B, st);
     float *x0 = scratch, *x1 = scratch + (size_t)B * W, *raw = scratch + (size_t)2 * B * W;
     dim3 grid((B + TM - 1) / TM, (W + TN - 1) / TN);
     fc_layer_kernel<true, false, false><<<grid, NTHREADS, 0, st>>>(nullptr, board, seats, S, p->w_in, p->b_in, nullptr,

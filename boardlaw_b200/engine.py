@@ -46,9 +46,11 @@ class SearchEngine:
             self.ws['logits'] = torch.full((B, T, A), np.nan, dtype=torch.float16, device=dev)
         self.exp_lut = _lib.exp_lut(dev)
         self.log_lut = _lib.log_lut(dev)
+        self.scratch = torch.empty((8 * _round_up(B, 64) * max(min(A, T - 1), 1),), dtype=torch.uint8, device=dev)
         fields = {k: self.ws[k].data_ptr() for k in self.ws}
         fields.setdefault('logits', None)
-        self.ctree = _lib.Tree(B=B, T=T, S=self.S, A=A, Sn=Sn, AP=self.AP, BP=self.BP, exp_lut=self.exp_lut.data_ptr(), **fields)
+        self.ctree = _lib.Tree(B=B, T=T, S=self.S, A=A, Sn=Sn, AP=self.AP, BP=self.BP, exp_lut=self.exp_lut.data_ptr(),
+                                scratch=self.scratch.data_ptr(), scratch_bytes=self.scratch.numel(), **fields)
         self._tp = ctypes.byref(self.ctree)
         # static I/O buffers (graph-replay safe)
         self.in_board = z((B, self.S, self.S), torch.uint8)

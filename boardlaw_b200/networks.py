@@ -56,6 +56,8 @@ class FCModel(nn.Module):
 
         self._pack_key = None
         self._pack = None
+        # False routes every shape through the CUDA-core fp32 kernels (net.cu) — used as the on-device cross-check
+        self.tensor_cores = True
 
     def sampler(self, logits, test=False):
         if test:
@@ -79,9 +81,14 @@ class FCModel(nn.Module):
                 alpha=torch.stack([f(getattr(r, 'α')) for r in res]) if res else torch.zeros((0,), device=dev),
                 w_pol=f(self.policy.core.weight), b_pol=f(self.policy.core.bias),
                 w_val=f(self.value.core.weight).reshape(-1), b_val=f(self.value.core.bias).reshape(-1))
+            tc = {}
+            if self.tensor_cores and W in (32, 64, 128, 256) and self.boardsize ** 2 + 1 <= 256:
+                blob, b_head = pack_tensor_core_operands(pack, self.boardsize)
+                pack['packed'], pack['b_head'] = blob, b_head
+                tc = dict(packed=blob.data_ptr(), b_head=b_head.data_ptr())
             cp = _lib.FCParams(
                 S=self.boardsize, W=W, D=len(res), precision=0 if self.precision == 'fp32' else 1,
-                **{k: t.data_ptr() for k, t in pack.items()}, packed=None)
+                **{k: t.data_ptr() for k, t in pack.items() if k not in ('packed', 'b_head')}, **tc)
             self._pack, self._pack_key, self._cparams = pack, key, cp
         return self._cparams
 
@@ -108,6 +115,40 @@ class FCModel(nn.Module):
         with torch.no_grad():
             logits, v = self.evaluate(worlds.board, worlds.seats)
         return arrdict.arrdict(logits=logits, v=v)
+
+
+KC = 32     # K elements per operand tile (net_tc.cu)
+
+
+def _split_tiles(w, n_pad, k_pad):
+    """(N,K) fp32 -> (k_pad/KC, 2, n_pad/8, KC/8, 8, 8) fp16: per K-chunk a hi block then a lo block, each in the UMMA
+    canonical K-major no-swizzle layout: element (n, k) at ((n/8)*(KC/8) + k/8)*64 + (n%8)*8 + k%8 halves."""
+    N, K = w.shape
+    full = w.new_zeros((n_pad, k_pad))
+    full[:N, :K] = w
+    hi = full.half()
+    lo = (full - hi.float()).half()
+    t = torch.stack([hi, lo])                                            # (2, n_pad, k_pad)
+    t = t.reshape(2, n_pad // 8, 8, k_pad // KC, KC // 8, 8)             # (2, n/8, n%8, chunk, k/8, k%8)
+    return t.permute(3, 0, 1, 4, 2, 5).contiguous()                      # (chunk, 2, n/8, k/8, n%8, k%8)
+
+
+def pack_tensor_core_operands(pack, boardsize):
+    """The weight blob fc_tc_kernel streams: layer 0 tiles, the residual layers' tiles, then the fused head
+    [policy ; value] — each weight split as hi = fp16(w), lo = fp16(w - hi)."""
+    A = boardsize * boardsize
+    W = pack['w_in'].shape[0]
+    k0p = (2 * A + KC - 1) // KC * KC
+    n_p = (A + 1 + 31) // 32 * 32
+    parts = [_split_tiles(pack['w_in'], W, k0p).reshape(-1)]
+    for k in range(pack['w_res'].shape[0]):
+        parts.append(_split_tiles(pack['w_res'][k], W, W).reshape(-1))
+    head = torch.cat([pack['w_pol'], pack['w_val'][None]], 0)            # (A+1, W)
+    parts.append(_split_tiles(head, n_p, W).reshape(-1))
+    b_head = pack['b_pol'].new_zeros((n_p,))
+    b_head[:A] = pack['b_pol']
+    b_head[A] = pack['b_val'][0]
+    return torch.cat(parts).contiguous(), b_head
 
 
 def synthetic_state_dict(boardsize, width, depth, seed=0):

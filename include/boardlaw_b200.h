@@ -126,7 +126,9 @@ typedef struct bl_fc_params {
     const float *b_pol;   /* (A,)     policy.core.bias    */
     const float *w_val;   /* (W,)     value.core.weight   */
     const float *b_val;   /* (1,)     value.core.bias     */
-    const void *packed;   /* tensor-core operand blob built by bl_fc_pack (NULL: CUDA-core path)   */
+    const void *packed;   /* tensor-core operand tiles (split-fp16, UMMA canonical K-major layout) built by the
+                             host packer, boardlaw_b200/networks.py:pack_tensor_core_operands; NULL: CUDA-core path */
+    const float *b_head;  /* (roundup(A+1,32),) = [policy bias (A), value bias, zeros]; with `packed`             */
 } bl_fc_params;
 
 /* Bytes of device scratch bl_fc_forward needs for a batch of B envs. */
@@ -168,6 +170,8 @@ typedef struct bl_tree {
     float *qrange;        /* (T+1,2) per-simulation (min,max) of w/(n+1e-4), ordered-int encoded    */
     uint64_t *counters;   /* (8,) policy evals, children seen, newton iters, descents, backup nodes */
     const float *exp_lut; /* (65536,)                                                               */
+    void *scratch;        /* device scratch for the descent's per-slot child lists                          */
+    int64_t scratch_bytes;/* >= 8 * roundup(B, 64) * min(A, T-1) bytes                                      */
 } bl_tree;
 
 /* Resets the workspace for a new search rooted at (board (B,S,S) u8, seats (B,) i32).  The in-kernel random
@@ -187,6 +191,14 @@ int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, const void 
  * draw them in-kernel from Philox4x32-10 keyed by (seed, move counter) and counted by (env, sim, node). */
 int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed,
                            bl_stream stream);
+
+/* Selects the descent kernel: 2 (default) = task-parallel descent (descend.cu), 1 = one lane per env in lock step
+ * (engine.cu; kept as an on-device cross-check).  Both produce identical results. */
+int bl_debug_set_descend_variant(int variant);
+
+/* Self test: counts operand pairs for which the shared-reciprocal division of descend.cu differs from the IEEE
+ * division (expected 0) over n_div x n_num pseudo-random pairs drawn from the descent's operand ranges. */
+int bl_selftest_division(uint64_t seed, int n_div, int n_num, uint64_t *mismatch, bl_stream stream);
 
 /* backup of the current leaves (boardlaw/mcts/cpp/cuda.cu:205-248) + the q-range scan used by the next
  * descent (transition_q's global min/max, cuda.cu:101-105), stored in qrange[sim+1]. */

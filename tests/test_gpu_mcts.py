@@ -89,8 +89,49 @@ def test_op_level_search_vs_oracle(S, B, T, W, D):
     assert torch.equal(gm.n_leaves().cpu(), o.n_leaves())
 
 
-@pytest.mark.parametrize('S,B,T,W,D', [(5, 256, 16, 32, 2), (9, 200, 64, 64, 4), (11, 70, 128, 32, 2), (13, 33, 32, 16, 1)])
-def test_engine_stepwise_vs_oracle(S, B, T, W, D):
+class ExtremeNet:
+    """Wraps the oracle network and pushes a few valid logits of every row into the range where exp() is denormal or
+    zero in fp32 (-70, -95, -110): exercises the engine's exact serial fallback for denormal-range lambda*pi."""
+
+    def __init__(self, net):
+        self.net = net
+
+    def __call__(self, world):
+        r = self.net(world)
+        logits = r.logits.clone()
+        for k, val in enumerate((-70., -95., -110.)):
+            idx = torch.where(world.valid, torch.arange(world.valid.shape[1])[None], 10 ** 6).kthvalue(k + 2, -1).indices
+            rows = torch.arange(logits.shape[0])
+            keep = world.valid[rows, idx]
+            logits[rows[keep], idx[keep]] = val
+        r.logits = logits
+        return r
+
+
+@pytest.mark.parametrize('variant', [2, 1])
+@pytest.mark.parametrize('S,B,T,W,D,extreme', [(5, 256, 16, 32, 2, False), (9, 200, 64, 64, 4, False), (11, 70, 128, 32, 2, False),
+                                               (13, 33, 32, 16, 1, False), (7, 130, 48, 32, 2, True)])
+def test_engine_stepwise_vs_oracle(S, B, T, W, D, extreme, variant):
+    from boardlaw_b200 import _lib
+    _lib.lib().bl_debug_set_descend_variant(variant)
+    try:
+        _engine_stepwise_vs_oracle(S, B, T, W, D, extreme)
+    finally:
+        _lib.lib().bl_debug_set_descend_variant(2)
+
+
+def test_shared_reciprocal_division():
+    """q0 = n*y, r = fma(-b, q0, n), q = fma(r, y, q0) with y = RN(1/b) against the IEEE division on 2^32 operand pairs
+    from the descent's ranges (divisors 2^-27..2^2 incl. all-ones / all-zeros significands, numerators 2^-100..2^-3)."""
+    from boardlaw_b200 import _lib
+    bad = torch.zeros(1, dtype=torch.int64, device='cuda')
+    dev = bad.device
+    _lib.check(_lib.lib().bl_selftest_division(1234, 1 << 16, 1 << 16, _lib.ptr(bad), _lib.stream_for(dev)), 'selftest')
+    torch.cuda.synchronize()
+    assert int(bad) == 0, f'{int(bad)} mismatching quotients'
+
+
+def _engine_stepwise_vs_oracle(S, B, T, W, D, extreme):
     """The fused engine's kernels (private layout: fp32 pi rows, child lists, per-sim q-range) stepped one simulation
     at a time with the oracle's network outputs injected: leaves, links, boards, statistics and the final root
     policy are identical to the oracle's after every simulation."""
@@ -100,6 +141,8 @@ def test_engine_stepwise_vs_oracle(S, B, T, W, D):
     sd = pyref.synth_state_dict(S, W, D, seed=4)
     w0 = gu.start_position(S, B, S * S // 3, seed=5)
     onet = pyref.FCNet(sd)
+    if extreme:
+        onet = ExtremeNet(onet)
     torch.manual_seed(6)
     A = S * S
 

@@ -13,10 +13,11 @@ pytestmark = pytest.mark.gpu
 ATOL = 1e-5
 
 
-def load_model(sd, S, W, D):
+def load_model(sd, S, W, D, tensor_cores=True):
     from boardlaw_b200 import heads
     from boardlaw_b200.networks import FCModel
     net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(S * S), width=W, depth=D)
+    net.tensor_cores = tensor_cores
     missing = net.load_state_dict(sd)          # same keys as the reference's state_dict
     assert not missing.missing_keys and not missing.unexpected_keys
     return net.cuda()
@@ -42,15 +43,21 @@ def test_forward_golden(S, W, D):
     compare(logits, v, torch.from_numpy(z['logits']), torch.from_numpy(z['v']))
 
 
-@pytest.mark.parametrize('S,W,D,B', [(9, 256, 4, 4096), (7, 128, 4, 1000), (13, 64, 2, 517), (3, 2, 4, 64), (11, 512, 8, 512)])
-def test_forward_vs_oracle(S, W, D, B):
+@pytest.mark.parametrize('tensor_cores', [True, False])
+@pytest.mark.parametrize('S,W,D,B', [(9, 256, 4, 4096), (7, 128, 4, 1000), (13, 64, 2, 517), (3, 2, 4, 64), (11, 512, 8, 512),
+                                     (5, 32, 2, 300), (9, 256, 0, 129), (9, 64, 1, 40000)])
+def test_forward_vs_oracle(S, W, D, B, tensor_cores):
+    """tensor_cores=True: tcgen05 split-fp16 kernel where the shape fits (W in 32/64/128/256), CUDA-core fp32 kernels
+    otherwise; False forces the CUDA-core path.  Both within 1e-5 of the fp32 CPU reference."""
     from oracle import pyref
     sd = pyref.synth_state_dict(S, W, D, seed=S + W)
     w = gu.start_position(S, B, S * S // 2, seed=W)
     ref = pyref.FCNet(sd)(w)
-    net = load_model(sd, S, W, D)
+    net = load_model(sd, S, W, D, tensor_cores)
     logits, v = net.evaluate(w.board.cuda(), w.seats.cuda())
-    compare(logits, v, ref.logits, ref.v)
+    torch.cuda.synchronize()
+    el, ev = compare(logits, v, ref.logits, ref.v)
+    print(f'S{S} W{W} D{D} tc={tensor_cores}: max |dlogit| {el:.2e}, max |dv| {ev:.2e}')
 
 
 def test_forward_through_world_api():
