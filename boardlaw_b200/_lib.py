@@ -13,7 +13,7 @@ import torch
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / 'libboardlaw_b200.so'
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class FCParams(Structure):
@@ -27,10 +27,8 @@ class FCParams(Structure):
 class Tree(Structure):
     """``bl_tree`` (include/boardlaw_b200.h)."""
     _fields_ = [('B', c_int), ('T', c_int), ('S', c_int), ('A', c_int), ('Sn', c_int), ('AP', c_int), ('BP', c_int),
-                ('pi', c_void_p), ('logits', c_void_p), ('board', c_void_p), ('seats', c_void_p),
-                ('terminal', c_void_p), ('parents', c_void_p), ('relation', c_void_p),
-                ('first_child', c_void_p), ('next_sib', c_void_p), ('n', c_void_p), ('w', c_void_p),
-                ('v', c_void_p), ('rewards', c_void_p), ('c_puct', c_void_p), ('leaf', c_void_p),
+                ('pi', c_void_p), ('logits', c_void_p), ('board', c_void_p), ('node', c_void_p), ('aux', c_void_p),
+                ('c_puct', c_void_p), ('leaf', c_void_p),
                 ('leaf_parent', c_void_p), ('leaf_action', c_void_p), ('prior', c_void_p), ('qrange', c_void_p),
                 ('counters', c_void_p), ('exp_lut', c_void_p), ('scratch', c_void_p), ('scratch_bytes', c_int64)]
 
@@ -52,6 +50,7 @@ SIGNATURES = {
     'bl_mcts_transition_q': (c_int, [P] * 4 + [c_int] * 3 + [P]),
     'bl_fc_scratch_bytes': (c_int64, [POINTER(FCParams), c_int]),
     'bl_fc_forward': (c_int, [POINTER(FCParams), P, P, P, P, P, c_int, P]),
+    'bl_tree_scratch_bytes': (c_int64, [POINTER(Tree)]),
     'bl_tree_reset': (c_int, [POINTER(Tree), P, P, c_float, P]),
     'bl_tree_set_eval': (c_int, [POINTER(Tree), c_int, P, P, c_int, P]),
     'bl_tree_descend_expand': (c_int, [POINTER(Tree), c_int, P, c_uint64, P]),

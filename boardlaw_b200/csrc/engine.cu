@@ -30,11 +30,12 @@ __global__ void __launch_bounds__(256) reset_kernel(bl_tree t, const uint8_t *__
     const long long BT = (long long)t.B * t.T;
     const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
     for (long long i = i0; i < BT; i += stride) {
-        t.parents[i] = -1; t.relation[i] = -1; t.first_child[i] = -1; t.next_sib[i] = -1;
-        t.n[i] = 0; t.terminal[i] = 0;
-        long long b = i / t.T;
-        t.seats[i] = (uint8_t)seats[b];
-        for (int s = 0; s < t.Sn; s++) { t.w[i * t.Sn + s] = 0; t.rewards[i * t.Sn + s] = 0; }
+        const long long b = i / t.T;
+        bl_node nd;
+        nd.parent = -1; nd.relation = -1; nd.first_child = -1; nd.next_sib = -1;
+        nd.n = 0; nd.w[0] = 0; nd.w[1] = 0; nd.seat = (uint8_t)seats[b]; nd.terminal = 0;
+        bl_st_node(t.node + i, nd);
+        reinterpret_cast<uint4 *>(t.aux)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     for (long long i = i0; i < (long long)t.B * t.A; i += stride) {
         long long b = i / t.A; int c = (int)(i - b * t.A);
@@ -49,28 +50,49 @@ __global__ void __launch_bounds__(256) reset_kernel(bl_tree t, const uint8_t *__
     }
 }
 
-// logits/v of one node per env -> pi row (+ prior when node 0) + v, rounding through half like decisions.half()
+// logits/v of one node per env -> pi row + row summary (+ prior when node 0) + v, rounding through half like
+// decisions.half() (boardlaw/mcts/__init__.py:135-136).  One warp per env.
 template <bool HALF_IN>
 __global__ void __launch_bounds__(256) set_eval_kernel(bl_tree t, int node, const void *__restrict__ logits_,
                                                        const void *__restrict__ v_) {
-    const long long n = (long long)t.B * t.A;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        long long b = i / t.A; int a = (int)(i - b * t.A);
-        int nd = node >= 0 ? node : t.leaf[b];
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < t.B; b += nwarps) {
+        const int nd = node >= 0 ? node : t.leaf[b];
         if (nd < 0) continue;
-        bl_half h = HALF_IN ? reinterpret_cast<const bl_half *>(logits_)[i] : bl_f2h(reinterpret_cast<const float *>(logits_)[i]);
-        t.pi[(b * t.T + nd) * t.AP + a] = t.exp_lut[h];
-        if (nd == 0) t.prior[i] = h;
-        if (t.logits) t.logits[(b * t.T + nd) * t.A + a] = h;
-        if (a < t.Sn) {
-            long long j = b * t.Sn + a;
-            bl_half hv = HALF_IN ? reinterpret_cast<const bl_half *>(v_)[j] : bl_f2h(reinterpret_cast<const float *>(v_)[j]);
-            t.v[(b * t.T + nd) * t.Sn + a] = hv;
+        const size_t slot = (size_t)b * t.T + nd;
+        float mx = 0.f, mn = BL_INF;
+        int fz = 255, lz = -1;
+        for (int a = lane; a < t.A; a += 32) {
+            const size_t i = (size_t)b * t.A + a;
+            const bl_half h = HALF_IN ? reinterpret_cast<const bl_half *>(logits_)[i] : bl_f2h(reinterpret_cast<const float *>(logits_)[i]);
+            const float p = t.exp_lut[h];
+            t.pi[slot * t.AP + a] = p;
+            if (nd == 0) t.prior[i] = h;
+            if (t.logits) t.logits[slot * t.A + a] = h;
+            if (p != 0.f) { mx = fmaxf(mx, p); mn = fminf(mn, p); fz = min(fz, a); lz = max(lz, a); }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            fz = min(fz, __shfl_xor_sync(0xffffffffu, fz, o));
+            lz = max(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+        }
+        if (lane == 0) {
+            bl_half hv[2];
+            for (int s = 0; s < 2; s++)
+                hv[s] = HALF_IN ? reinterpret_cast<const bl_half *>(v_)[(size_t)b * 2 + s] : bl_f2h(reinterpret_cast<const float *>(v_)[(size_t)b * 2 + s]);
+            uint32_t *ax = reinterpret_cast<uint32_t *>(t.aux + slot);
+            ax[1] = (uint32_t)hv[0] | ((uint32_t)hv[1] << 16);
+            // minnz_hi truncates the smallest nonzero pi downwards: the tiny-value test it feeds errs on the safe side
+            reinterpret_cast<uint2 *>(ax)[1] = make_uint2(__float_as_uint(mx), (__float_as_uint(mn) >> 16) | ((uint32_t)(fz & 255) << 16) |
+                                                                                  ((uint32_t)((lz < 0 ? 0 : lz) & 255) << 24));
         }
     }
 }
 
-// ---- descend + expand + env step -------------------------------------------------------------------------------
+// ---- descend + expand + env step, lock-step variant (on-device cross-check of descend.cu) ---------------------------
 struct Smem {
     float *top, *q;        // [A][FP]
     uint8_t *bd, *stk;     // [A][BPITCH]
@@ -90,7 +112,7 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
     extern __shared__ __align__(16) uint8_t raw[];
     Smem sm = carve(raw, t.A);
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-    const int A = t.A, T = t.T, Sn = t.Sn;
+    const int A = t.A, T = t.T;
     const int b = blockIdx.x * ENT + tid;
     const int bw = blockIdx.x * ENT + wbase;               // first env of this warp
     const bool in_range = b < t.B;
@@ -107,7 +129,9 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
     unsigned c_evals = 0, c_children = 0, c_iters = 0;
 
     while (true) {
-        bool active = cur >= 0 && !t.terminal[node0 + cur];
+        bl_node nd;
+        bool active = false;
+        if (cur >= 0) { nd = bl_ld_node(t.node + node0 + cur); active = !nd.terminal; }
         unsigned mask = __ballot_sync(0xffffffffu, active);
         if (!mask) break;
         // cooperative, coalesced load of each active lane's pi row into its shared-memory column
@@ -119,13 +143,14 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
         }
         __syncwarp();
         if (active) {
-            const int seat = t.seats[node0 + cur];
+            const int seat = nd.seat;
             int N = 0, nc = 0;
-            for (int c = t.first_child[node0 + cur]; c >= 0; c = t.next_sib[node0 + c]) {
-                int16_t nn = t.n[node0 + c];
-                q[t.relation[node0 + c] * FP] = qn(t.w[(node0 + c) * Sn + seat], nn);
-                N += nn;
+            for (int c = nd.first_child; c >= 0;) {
+                const bl_node ch = bl_ld_node(t.node + node0 + c);
+                q[ch.relation * FP] = qn(ch.w[seat], ch.n);
+                N += ch.n;
                 nc++;
+                c = ch.next_sib;
             }
             N += A - nc;                                        // every child-less action counts 1 (cuda.cu:91)
             const float lambda = bl_lambda(c_puct, N, A);
@@ -138,115 +163,84 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
             action = bl_sample(top, q, FP, A, alpha, r);
             parent = cur;
             int next = -1;
-            for (int c = t.first_child[node0 + cur]; c >= 0; c = t.next_sib[node0 + c]) {
-                int rel = t.relation[node0 + c];
-                q[rel * FP] = 0.f;                              // leave the column zeroed for the next node
-                if (rel == action) next = c;
+            for (int c = nd.first_child; c >= 0;) {
+                const bl_node ch = bl_ld_node(t.node + node0 + c);
+                q[ch.relation * FP] = 0.f;                      // leave the column zeroed for the next node
+                if (ch.relation == action) next = c;
+                c = ch.next_sib;
             }
             cur = action >= 0 ? next : -2;                      // -2: no positive-probability action (error)
             c_evals++; c_children += nc; c_iters += it;
         }
         __syncwarp();
     }
-
-    // expand (boardlaw/mcts/__init__.py:117-122)
-    const bool ok = in_range && action >= 0 && cur != -2;
-    int leaf = -1;
-    if (ok) {
-        if (cur >= 0) leaf = cur;                               // stopped at an existing terminal child: reuse its slot
-        else {
-            leaf = sim;
-            t.parents[node0 + sim] = (int16_t)parent;
-            t.relation[node0 + sim] = (int16_t)action;
-            t.next_sib[node0 + sim] = t.first_child[node0 + parent];
-            t.first_child[node0 + parent] = (int16_t)sim;
-        }
-    } else if (in_range) {
-        atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_ERRORS), 1ull);
-    }
     if (in_range) {
-        t.leaf[b] = (int16_t)leaf;
+        t.leaf[b] = (int16_t)(cur == -2 ? -1 : cur);            // existing terminal child, or -1
         t.leaf_parent[b] = (int16_t)parent;
-        t.leaf_action[b] = (int16_t)action;
-    }
-
-    // env step of the parent's board into the leaf slot (boardlaw/mcts/__init__.py:124-129, Hex.step)
-    unsigned omask = __ballot_sync(0xffffffffu, ok);
-    for (unsigned m = omask; m; m &= m - 1) {
-        int l = __ffs(m) - 1;
-        int pl = __shfl_sync(0xffffffffu, parent, l);
-        const uint8_t *row = t.board + ((size_t)(bw + l) * T + pl) * t.BP;
-        for (int c = lane; c < A; c += 32) sm.bd[c * BPITCH + wbase + l] = row[c];
-    }
-    __syncwarp();
-    if (ok) {
-        const int seat = t.seats[node0 + parent];
-        int win = bl_hex_place<uint8_t>(sm.bd + tid, sm.stk + tid, BPITCH, t.S, seat, action);
-        float r0 = win == 1 ? 1.f : (win == 2 ? -1.f : 0.f), r1 = win == 1 ? -1.f : (win == 2 ? 1.f : 0.f);
-        t.rewards[(node0 + leaf) * Sn + 0] = bl_f2h(r0);
-        t.rewards[(node0 + leaf) * Sn + 1] = bl_f2h(r1);
-        t.terminal[node0 + leaf] = win != 0;
-        t.seats[node0 + leaf] = win ? 0 : (uint8_t)(1 - seat);
-        if (win)
-            for (int c = 0; c < A; c++) sm.bd[c * BPITCH + tid] = 0;   // auto-reset (hex/__init__.py:185-188)
-    }
-    __syncwarp();
-    for (unsigned m = omask; m; m &= m - 1) {
-        int l = __ffs(m) - 1;
-        int ll = __shfl_sync(0xffffffffu, leaf, l);
-        uint8_t *row = t.board + ((size_t)(bw + l) * T + ll) * t.BP;
-        for (int c = lane; c < A; c += 32) row[c] = sm.bd[c * BPITCH + wbase + l];
+        t.leaf_action[b] = (int16_t)(cur == -2 ? -1 : action);
     }
     bl_count(t.counters, C_EVALS, c_evals);
     bl_count(t.counters, C_CHILDREN, c_children);
     bl_count(t.counters, C_ITERS, c_iters);
-    bl_count(t.counters, C_DESCENTS, ok ? 1u : 0u);
+    bl_count(t.counters, C_DESCENTS, (in_range && action >= 0 && cur != -2) ? 1u : 0u);
 }
 
 // ---- backup + q-range scan ----------------------------------------------------------------------------------------
-constexpr int BNT = 128;
-__global__ void __launch_bounds__(BNT) backup_kernel(bl_tree t, int sim) {
-    const int b = blockIdx.x * BNT + threadIdx.x;
-    const int T = t.T, Sn = t.Sn;
-    unsigned visited = 0;
-    if (b < t.B) {
-        const size_t base = (size_t)b * T;
-        int cur = t.leaf[b];
-        float val[2] = {0.f, 0.f};
-        if (cur >= 0) { val[0] = bl_h2f(t.v[(base + cur) * Sn]); val[1] = bl_h2f(t.v[(base + cur) * Sn + 1]); }
-        while (cur >= 0) {
-            const size_t node = base + cur;
-            const bool term = t.terminal[node];
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                if (term) val[s] = 0.f;
-                val[s] = __fadd_rn(val[s], bl_h2f(t.rewards[node * Sn + s]));
-                t.w[node * Sn + s] = bl_f2h(__fadd_rn(bl_h2f(t.w[node * Sn + s]), bl_h2f(bl_f2h(val[s]))));
+// One CTA per 32 envs: warp 0 walks the 32 leaf->root paths (one 2 x 128-bit load per step), then all warps scan the CTA's
+// 32*T node records for the (min,max) of w/(n+1e-4) that the NEXT descent normalises with (slot sim+1).
+constexpr int BK_ENVS = 32, BK_THREADS = 128;
+__global__ void __launch_bounds__(BK_THREADS) backup_kernel(bl_tree t, int sim) {
+    const int T = t.T;
+    const int b0 = blockIdx.x * BK_ENVS;
+    if (threadIdx.x < BK_ENVS) {
+        const int b = b0 + threadIdx.x;
+        unsigned visited = 0;
+        if (b < t.B) {
+            const size_t base = (size_t)b * T;
+            int cur = t.leaf[b];
+            float val[2] = {0.f, 0.f};
+            bl_node nd;
+            bl_aux ax;
+            if (cur >= 0) {
+                nd = bl_ld_node(t.node + base + cur);
+                ax = bl_ld_aux(t.aux + base + cur);
+                val[0] = bl_h2f(ax.v[0]); val[1] = bl_h2f(ax.v[1]);
             }
-            t.n[node] = (int16_t)(t.n[node] + Sn);              // quirk: +1 per seat (cuda.cu:228)
-            cur = t.parents[node];
-            visited++;
+            while (cur >= 0) {
+                const int next = nd.parent;
+                bl_node pn;
+                bl_aux pa;
+                if (next >= 0) { pn = bl_ld_node(t.node + base + next); pa = bl_ld_aux(t.aux + base + next); }   // in flight during the update
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    if (nd.terminal) val[s] = 0.f;
+                    val[s] = __fadd_rn(val[s], bl_h2f(ax.rewards[s]));
+                    nd.w[s] = bl_f2h(__fadd_rn(bl_h2f(nd.w[s]), bl_h2f(bl_f2h(val[s]))));
+                }
+                nd.n = (int16_t)(nd.n + t.Sn);                      // quirk: +1 per seat (cuda.cu:228)
+                bl_st_node_stats(t.node + base + cur, nd);
+                cur = next; nd = pn; ax = pa;
+                visited++;
+            }
         }
+        bl_count(t.counters, C_BACKUP_NODES, visited);
     }
     __syncthreads();
-    // q-range of the block's envs (contiguous (w, n) spans): feeds the NEXT descent (slot sim+1)
-    const int nb = min(BNT, t.B - blockIdx.x * BNT);
-    const size_t first = (size_t)blockIdx.x * BNT * T;
+    const int nb = min(BK_ENVS, t.B - b0);
+    const bl_node *first = t.node + (size_t)b0 * T;
     float lo = BL_INF, hi = -BL_INF;
-    for (int i = threadIdx.x; i < nb * T; i += BNT) {
-        int16_t nn = t.n[first + i];
-        const __half2 ww = reinterpret_cast<const __half2 *>(t.w)[first + i];
-        float q0 = bl_qraw(__half_as_ushort(__low2half(ww)), nn), q1 = bl_qraw(__half_as_ushort(__high2half(ww)), nn);
+    for (int i = threadIdx.x; i < nb * T; i += BK_THREADS) {
+        const bl_node nd = bl_ld_node(first + i);
+        const float q0 = bl_qraw(nd.w[0], nd.n), q1 = bl_qraw(nd.w[1], nd.n);
         lo = fminf(lo, fminf(q0, q1));
         hi = fmaxf(hi, fmaxf(q0, q1));
     }
-    int klo = __reduce_min_sync(0xffffffffu, bl_f2ord(lo)), khi = __reduce_max_sync(0xffffffffu, bl_f2ord(hi));
+    const int klo = __reduce_min_sync(0xffffffffu, bl_f2ord(lo)), khi = __reduce_max_sync(0xffffffffu, bl_f2ord(hi));
     if (bl_lane() == 0) {
         int *qr = reinterpret_cast<int *>(t.qrange) + 2 * (sim + 1);
         atomicMin(qr, klo);
         atomicMax(qr + 1, khi);
     }
-    bl_count(t.counters, C_BACKUP_NODES, visited);
 }
 
 // ---- root ------------------------------------------------------------------------------------------------------------
@@ -271,13 +265,15 @@ __global__ void __launch_bounds__(ENT) root_kernel(bl_tree t, int sim, const bl_
     if (!in_range) return;
     for (int a = 0; a < A; a++) q[a * FP] = 0.f;
     const bl_qnorm qn(t.qrange + 2 * sim);
-    const int seat = t.seats[node0];
+    const bl_node root = bl_ld_node(t.node + node0);
+    const int seat = root.seat;
     int N = 0, nc = 0;
-    for (int c = t.first_child[node0]; c >= 0; c = t.next_sib[node0 + c]) {
-        int16_t nn = t.n[node0 + c];
-        q[t.relation[node0 + c] * FP] = qn(t.w[(node0 + c) * Sn + seat], nn);
-        N += nn;
+    for (int c = root.first_child; c >= 0;) {
+        const bl_node ch = bl_ld_node(t.node + node0 + c);
+        q[ch.relation * FP] = qn(ch.w[seat], ch.n);
+        N += ch.n;
         nc++;
+        c = ch.next_sib;
     }
     N += A - nc;
     const float lambda = bl_lambda(bl_h2f(t.c_puct[b]), N, A);
@@ -287,9 +283,13 @@ __global__ void __launch_bounds__(ENT) root_kernel(bl_tree t, int sim, const bl_
     // probs -> half -> log -> half (MCTS.root, boardlaw/mcts/__init__.py:142-149); log through the host-libm table
     for (int a = 0; a < A; a++)
         logits[(size_t)b * A + a] = log_lut[bl_f2h(bl_prob(top[a * FP], q[a * FP], alpha))];
-    for (int s = 0; s < Sn; s++) v[(size_t)b * Sn + s] = t.v[node0 * Sn + s];
+    const bl_aux ra = bl_ld_aux(t.aux + node0);
+    for (int s = 0; s < Sn; s++) v[(size_t)b * Sn + s] = ra.v[s];
     int leaves = 0;
-    for (int k = 1; k < T; k++) leaves += (t.parents[node0 + k] != -1) && (t.first_child[node0 + k] == -1);
+    for (int k = 1; k < T; k++) {
+        const bl_node nd = bl_ld_node(t.node + node0 + k);
+        leaves += (nd.parent != -1) && (nd.first_child == -1);
+    }
     n_leaves[b] = leaves;
 }
 
@@ -301,10 +301,10 @@ __global__ void __launch_bounds__(256) children_dense_kernel(bl_tree t, int16_t 
 __global__ void __launch_bounds__(256) children_scatter_kernel(bl_tree t, int16_t *__restrict__ children) {
     const long long n = (long long)t.B * t.T;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        int p = t.parents[i];
-        if (p < 0) continue;
+        const bl_node nd = bl_ld_node(t.node + i);
+        if (nd.parent < 0) continue;
         long long b = i / t.T; int k = (int)(i - b * t.T);
-        children[((b * t.T) + p) * t.A + t.relation[i]] = (int16_t)k;
+        children[((b * t.T) + nd.parent) * t.A + nd.relation] = (int16_t)k;
     }
 }
 
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) gather_leaves_kernel(bl_tree t, int node,
         long long b = i / t.A; int c = (int)(i - b * t.A);
         int nd = node >= 0 ? node : max((int)t.leaf[b], 0);
         board[i] = t.board[(b * t.T + nd) * t.BP + c];
-        if (c == 0) seats[b] = t.seats[b * t.T + nd];
+        if (c == 0) seats[b] = t.node[b * t.T + nd].seat;
     }
 }
 
@@ -347,7 +347,7 @@ extern "C" int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, 
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (node >= t->T) return -1;
-    int grid = grid1d((long long)t->B * t->A, 256);
+    int grid = grid1d((long long)t->B * 32, 256);            // one warp per env
     if (inputs_are_half) set_eval_kernel<true><<<grid, 256, 0, bl_cu(stream)>>>(*t, node, logits, v);
     else set_eval_kernel<false><<<grid, 256, 0, bl_cu(stream)>>>(*t, node, logits, v);
     BL_LAUNCH_CHECK();
@@ -357,7 +357,7 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (sim < 1 || sim >= t->T) return -1;
-    if (g_descend_variant == 2) return bl_descend_v2(t, sim, rands, seed, bl_cu(stream));
+    if (g_descend_variant == 2) return bl_descend_v3(t, sim, rands, seed, bl_cu(stream));
     size_t smem = descend_smem(t->A);
     if (smem > 227 * 1024) return -2;
     if (smem > 48 * 1024) {
@@ -365,7 +365,8 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
         if (e != cudaSuccess) return (int)e;
     }
     descend_expand_kernel<<<(t->B + ENT - 1) / ENT, ENT, smem, bl_cu(stream)>>>(*t, sim, rands, seed);
-    BL_LAUNCH_CHECK();
+    if (cudaError_t e = cudaGetLastError()) return (int)e;
+    return bl_expand_step(t, sim, bl_cu(stream));
 }
 
 extern "C" int bl_debug_set_descend_variant(int variant) {
@@ -378,7 +379,7 @@ extern "C" int bl_tree_backup(const bl_tree *t, int sim, bl_stream stream) {
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (sim < 1 || sim >= t->T) return -1;
-    backup_kernel<<<(t->B + BNT - 1) / BNT, BNT, 0, bl_cu(stream)>>>(*t, sim);
+    backup_kernel<<<(t->B + BK_ENVS - 1) / BK_ENVS, BK_THREADS, 0, bl_cu(stream)>>>(*t, sim);
     BL_LAUNCH_CHECK();
 }
 

@@ -5,6 +5,34 @@
 // bl_tree.counters slots
 enum { C_EVALS = 0, C_CHILDREN = 1, C_ITERS = 2, C_DESCENTS = 3, C_BACKUP_NODES = 4, C_ERRORS = 5, C_MOVE = 6, C_QUEUE = 7 };
 
+static_assert(sizeof(bl_node) == 16 && sizeof(bl_aux) == 16, "tree records are 16 bytes");
+
+// 128-bit record loads/stores (records are 16-byte aligned: the arrays come from the caller's allocator, >= 256 B aligned)
+__device__ __forceinline__ bl_node bl_ld_node(const bl_node *p) {
+    union { uint4 u; bl_node n; } x;
+    x.u = *reinterpret_cast<const uint4 *>(p);
+    return x.n;
+}
+__device__ __forceinline__ void bl_st_node(bl_node *p, const bl_node &n) {
+    union { uint4 u; bl_node n; } x;
+    x.n = n;
+    *reinterpret_cast<uint4 *>(p) = x.u;
+}
+__device__ __forceinline__ bl_aux bl_ld_aux(const bl_aux *p) {
+    union { uint4 u; bl_aux a; } x;
+    x.u = *reinterpret_cast<const uint4 *>(p);
+    return x.a;
+}
+// the statistics half of a node record (n, w, seat, terminal) as one 8-byte store
+__device__ __forceinline__ void bl_st_node_stats(bl_node *p, const bl_node &n) {
+    union { uint4 u; bl_node n; } x;
+    x.n = n;
+    reinterpret_cast<uint2 *>(p)[1] = make_uint2(x.u.z, x.u.w);
+}
+__device__ __forceinline__ float bl_minnz(const bl_aux &a) { return __uint_as_float((uint32_t)a.minnz_hi << 16); }
+
 // descend.cu: task-parallel descent (writes t.leaf = existing terminal child or -1, t.leaf_parent, t.leaf_action)
 // followed by expand + env step.  Returns a cudaError_t / negative argument error.
-int bl_descend_v2(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
+int bl_descend_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
+// descend.cu: expand + env step of the descents recorded in t.leaf / leaf_parent / leaf_action
+int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st);

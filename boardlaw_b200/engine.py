@@ -31,26 +31,35 @@ class SearchEngine:
         self.seed = seed
         B, T, A, Sn, dev = self.B, self.T, self.A, self.Sn, self.device
         z = lambda shape, dtype: torch.zeros(shape, dtype=dtype, device=dev)
+        # two 16-byte records per (env, node) — bl_node / bl_aux of include/boardlaw_b200.h — so that a node visit is
+        # one 128-bit load; the reference-named tensors below are strided views into them
+        node = z((B, T, 8), torch.int16)
+        aux = z((B, T, 8), torch.int16)
+        node_bytes = node.view(torch.uint8)
         self.ws = arrdict.arrdict(
             pi=z((B, T, self.AP), torch.float32),
             board=z((B, T, self.BP), torch.uint8),
-            seats=z((B, T), torch.uint8),
-            terminal=z((B, T), torch.uint8),
-            parents=z((B, T), torch.int16), relation=z((B, T), torch.int16),
-            first_child=z((B, T), torch.int16), next_sib=z((B, T), torch.int16),
-            n=z((B, T), torch.int16), w=z((B, T, Sn), torch.float16), v=z((B, T, Sn), torch.float16),
-            rewards=z((B, T, Sn), torch.float16), c_puct=z((B,), torch.float16),
+            node=node, aux=aux,
+            c_puct=z((B,), torch.float16),
             leaf=z((B,), torch.int16), leaf_parent=z((B,), torch.int16), leaf_action=z((B,), torch.int16),
             prior=z((B, A), torch.float16), qrange=z((T + 1, 2), torch.float32), counters=z((8,), torch.int64))
         if mirror_logits:
             self.ws['logits'] = torch.full((B, T, A), np.nan, dtype=torch.float16, device=dev)
+        views = arrdict.arrdict(
+            parents=node[:, :, 0], relation=node[:, :, 1], first_child=node[:, :, 2], next_sib=node[:, :, 3],
+            n=node[:, :, 4], w=node[:, :, 5:7].view(torch.float16),
+            seats=node_bytes[:, :, 14], terminal=node_bytes[:, :, 15],
+            rewards=aux[:, :, 0:2].view(torch.float16), v=aux[:, :, 2:4].view(torch.float16))
         self.exp_lut = _lib.exp_lut(dev)
         self.log_lut = _lib.log_lut(dev)
-        self.scratch = torch.empty((8 * _round_up(B, 64) * max(min(A, T - 1), 1),), dtype=torch.uint8, device=dev)
         fields = {k: self.ws[k].data_ptr() for k in self.ws}
         fields.setdefault('logits', None)
         self.ctree = _lib.Tree(B=B, T=T, S=self.S, A=A, Sn=Sn, AP=self.AP, BP=self.BP, exp_lut=self.exp_lut.data_ptr(),
-                                scratch=self.scratch.data_ptr(), scratch_bytes=self.scratch.numel(), **fields)
+                                scratch=None, scratch_bytes=0, **fields)
+        nscratch = int(_lib.lib().bl_tree_scratch_bytes(ctypes.byref(self.ctree)))
+        self.scratch = torch.empty((max(nscratch, 16),), dtype=torch.uint8, device=dev)
+        self.ctree.scratch, self.ctree.scratch_bytes = self.scratch.data_ptr(), self.scratch.numel()
+        self.ws.update(views)
         self._tp = ctypes.byref(self.ctree)
         # static I/O buffers (graph-replay safe)
         self.in_board = z((B, self.S, self.S), torch.uint8)

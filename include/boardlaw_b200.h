@@ -145,34 +145,51 @@ int bl_fc_forward(const bl_fc_params *p, const uint8_t *board, const int32_t *se
  * The workspace arrays are allocated by the caller (torch) and described by bl_tree.
  * ------------------------------------------------------------------------------------------- */
 
+/* One record per (env, node); 16 bytes so that a node visit is a single 128-bit load. */
+typedef struct bl_node {
+    int16_t parent;       /* -1 = none                                                              */
+    int16_t relation;     /* action that led here                                                   */
+    int16_t first_child;  /* head of the child list, -1 = none                                      */
+    int16_t next_sib;     /* next sibling                                                           */
+    int16_t n;            /* visit count (incremented Sn per visit, as the reference)               */
+    bl_half w[2];         /* accumulated value per seat                                             */
+    uint8_t seat;         /* seat to move                                                           */
+    uint8_t terminal;
+} bl_node;
+
+/* Second 16-byte record per (env, node): what only the backup and the row load need. */
+typedef struct bl_aux {
+    bl_half rewards[2];
+    bl_half v[2];
+    float max_pi;         /* max of the node's pi row (seeds alpha: max_a RN(lambda*pi_a) = RN(lambda*max_pi)) */
+    uint16_t minnz_hi;    /* upper 16 bits of the smallest nonzero pi (truncated, i.e. conservative)  */
+    uint8_t first_nz;     /* first / last action with pi != 0                                        */
+    uint8_t last_nz;
+} bl_aux;
+
 typedef struct bl_tree {
     int B, T, S, A, Sn;
     int AP;               /* row pitch of pi in floats (A rounded up to a multiple of 4)            */
     int BP;               /* row pitch of board in bytes (A rounded up to a multiple of 16)         */
-    float *pi;            /* (B,T,AP) exp(logits) as fp32, value of exp_lut[half(logit)]             */
+    float *pi;            /* (B,T,AP) exp(logits) as fp32, value of exp_lut[half(logit)]; pad = 0    */
     bl_half *logits;      /* (B,T,A) half or NULL: reference-layout mirror (kept only in debug mode) */
     uint8_t *board;       /* (B,T,BP) u8 absolute-frame boards                                      */
-    uint8_t *seats;       /* (B,T)  u8 seat to move                                                 */
-    uint8_t *terminal;    /* (B,T)  u8                                                              */
-    int16_t *parents;     /* (B,T)  i16, -1 = none                                                  */
-    int16_t *relation;    /* (B,T)  i16 action that led here                                        */
-    int16_t *first_child; /* (B,T)  i16 head of the child list, -1 = none                           */
-    int16_t *next_sib;    /* (B,T)  i16 next sibling                                                */
-    int16_t *n;           /* (B,T)  i16 visit counts (incremented Sn per visit, as the reference)   */
-    bl_half *w;           /* (B,T,Sn) half                                                          */
-    bl_half *v;           /* (B,T,Sn) half                                                          */
-    bl_half *rewards;     /* (B,T,Sn) half                                                          */
+    bl_node *node;        /* (B,T)                                                                  */
+    bl_aux *aux;          /* (B,T)                                                                  */
     bl_half *c_puct;      /* (B,)   half                                                            */
     int16_t *leaf;        /* (B,)   i16 leaf of the current simulation                              */
     int16_t *leaf_parent; /* (B,)   i16                                                             */
     int16_t *leaf_action; /* (B,)   i16                                                             */
     bl_half *prior;       /* (B,A)  half: the (noised) root logits as stored, = decisions.logits[:,0]       */
     float *qrange;        /* (T+1,2) per-simulation (min,max) of w/(n+1e-4), ordered-int encoded    */
-    uint64_t *counters;   /* (8,) policy evals, children seen, newton iters, descents, backup nodes */
+    uint64_t *counters;   /* (8,) policy evals, children seen, newton iters, descents, backup nodes, errors, move, queue */
     const float *exp_lut; /* (65536,)                                                               */
-    void *scratch;        /* device scratch for the descent's per-slot child lists                          */
-    int64_t scratch_bytes;/* >= 8 * roundup(B, 64) * min(A, T-1) bytes                                      */
+    void *scratch;        /* device scratch for the descent's per-lane child lists                          */
+    int64_t scratch_bytes;/* >= bl_tree_scratch_bytes(t)                                                    */
 } bl_tree;
+
+/* Bytes of `scratch` the descent needs for a tree of this shape. */
+int64_t bl_tree_scratch_bytes(const bl_tree *t);
 
 /* Resets the workspace for a new search rooted at (board (B,S,S) u8, seats (B,) i32).  The in-kernel random
  * stream is keyed by (seed, counters[6]); the host stores the move index in counters[6] before each search. */
@@ -192,8 +209,9 @@ int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, const void 
 int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed,
                            bl_stream stream);
 
-/* Selects the descent kernel: 2 (default) = task-parallel descent (descend.cu), 1 = one lane per env in lock step
- * (engine.cu; kept as an on-device cross-check).  Both produce identical results. */
+/* Selects the descent kernel: 2 (default) = task-parallel descent with register-resident rows (descend.cu),
+ * 1 = one lane per env in lock step, reference loops verbatim (engine.cu; kept as an on-device cross-check).
+ * Both produce identical results. */
 int bl_debug_set_descend_variant(int variant);
 
 /* Self test: counts operand pairs for which the shared-reciprocal division of descend.cu differs from the IEEE
