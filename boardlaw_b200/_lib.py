@@ -13,7 +13,7 @@ import torch
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / 'libboardlaw_b200.so'
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class FCParams(Structure):
@@ -27,7 +27,7 @@ class FCParams(Structure):
 class Tree(Structure):
     """``bl_tree`` (include/boardlaw_b200.h)."""
     _fields_ = [('B', c_int), ('T', c_int), ('S', c_int), ('A', c_int), ('Sn', c_int), ('AP', c_int), ('BP', c_int),
-                ('pi', c_void_p), ('logits', c_void_p), ('board', c_void_p), ('node', c_void_p), ('aux', c_void_p),
+                ('pi', c_void_p), ('logits', c_void_p), ('board', c_void_p), ('node', c_void_p), ('aux', c_void_p), ('parent_of', c_void_p),
                 ('c_puct', c_void_p), ('leaf', c_void_p),
                 ('leaf_parent', c_void_p), ('leaf_action', c_void_p), ('prior', c_void_p), ('qrange', c_void_p),
                 ('counters', c_void_p), ('exp_lut', c_void_p), ('scratch', c_void_p), ('scratch_bytes', c_int64)]
@@ -56,6 +56,7 @@ SIGNATURES = {
     'bl_tree_descend_expand': (c_int, [POINTER(Tree), c_int, P, c_uint64, P]),
     'bl_tree_backup': (c_int, [POINTER(Tree), c_int, P]),
     'bl_debug_set_descend_variant': (c_int, [c_int]),
+    'bl_debug_set_phase_profile': (c_int, [P]),
     'bl_selftest_division': (c_int, [c_uint64, c_int, c_int, P, P]),
     'bl_tree_eval_scratch_bytes': (c_int64, [POINTER(Tree), POINTER(FCParams)]),
     'bl_tree_eval_leaves': (c_int, [POINTER(Tree), POINTER(FCParams), c_int, P, P]),

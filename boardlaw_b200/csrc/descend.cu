@@ -44,147 +44,288 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0,
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int NCH>
+// service gate: the visit / sample / advance phases run when at least GATE_NUM/GATE_DEN of the warp's live lanes wait for them
+// (or nobody is in a pass); a lane therefore idles a trip or two now and then, and the warp does not pay the phases'
+// latency on every trip
+#ifndef BL_GATE_NUM
+#define BL_GATE_NUM 1
+#define BL_GATE_DEN 3
+#endif
+
+template <int NCH, bool PROF>
 __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_t seed,
-                                                        ChildEntry *__restrict__ clists, int cap) {
+                                                        ChildEntry *__restrict__ clists, int cap, unsigned long long *prof) {
     constexpr int PS = 4 * NCH;                         // row pitch in floats; NCH odd => conflict-free 128-bit lane-private rows
+    constexpr int KS = NCH;                             // child entries (16 B each) kept in the lane's shared-memory row (rest: global scratch)
+    constexpr int NW = (PS + 63) / 64;                  // 64-bit words of the child-position mask
+    constexpr int MW = 4;                               // 64-bit words of the children-of-this-node mask (T <= 256; else list walk)
+    constexpr int STEP0 = PS >= 128 ? 128 : (PS >= 64 ? 64 : (PS >= 32 ? 32 : (PS >= 16 ? 16 : 8)));
     extern __shared__ float4 smem4[];
     const int A = t.A, T = t.T;
     const int lane = threadIdx.x;
-    float *ps = reinterpret_cast<float *>(smem4) + lane * PS;       // staging row / S child terms in, running S sums out
+    float *ps = reinterpret_cast<float *>(smem4) + lane * PS;       // S child terms in, running S sums out
     float *pg = ps + 32 * PS;                                       // g child terms
+    float4 *pe4 = reinterpret_cast<float4 *>(pg + 32 * PS);         // child entries {q, top, action | id << 8, -}; raw node records while in flight
     float4 *ps4 = reinterpret_cast<float4 *>(ps);
-    const uint32_t ps_addr = smem_u32(ps), pg_addr = smem_u32(pg);
+    const uint32_t ps_addr = smem_u32(ps), pg_addr = smem_u32(pg), pe_addr = smem_u32(pe4);
     ChildEntry *cl = clists + ((size_t)blockIdx.x * 32 + lane) * cap;
     const bl_qnorm qn(t.qrange + 2 * sim);
     const uint64_t move = t.counters[C_MOVE];
+    const uint64_t keep = bl_policy_keep();
     int *queue = reinterpret_cast<int *>(t.counters + C_QUEUE);
     const int nrow4 = t.AP >> 2;
+    const int TP = (T + 7) & ~7;
+    const bool scan_ok = T <= 64 * MW;
+    const int nscan = (sim + 7) >> 3;                 // 16-byte chunks of the parent row that can hold nodes created so far
 
-    u64 tp[2 * NCH];                                  // lambda*pi of the current node, element pairs; sign set where a child exists
-    ChildEntry e0 = {0.f, 0.f, 0, -1}, e1 = {0.f, 0.f, 0, -1};      // the first two children live in registers, the rest in `cl`
+    u64 tp[2 * NCH];                                  // lambda*pi of the current node, element pairs
+    u64 cm[NW];                                       // bit a set: action a has a child
     int b = -1, cur = -1, parent = 0, action = -1, state = ST_VISIT, nc = 0, it = 0;
     float alpha = 1.f, error = 0.f, r = 0.f;
-    u64 cmask = 0;                                    // bit c set: chunk c holds a child
     uint32_t nzpos = 0;                               // first_nz | last_nz << 8 of the current row
-    bool exhausted = false;                           // warp-uniform
+    bool exhausted = false;                           // warp-uniform: the queue has nothing left
+    const bool all_resident = (long long)gridDim.x * 32 >= t.B;   // every env has a lane: no queue, env = global lane index
     unsigned c_evals = 0, c_children = 0, c_iters = 0, c_desc = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) cm[w] = 0;
+    // optional phase clock (bl_debug_set_phase_profile): cycles per phase summed over warps, for DESIGN.md's latency budget
+    long long pc[PROF ? 12 : 1], tlast = PROF ? clock64() : 0;
+#pragma unroll
+    for (int k = 0; k < (PROF ? 12 : 1); k++) pc[k] = 0;
+#define tick(k) do { if (PROF) { const long long now_ = clock64(); pc[k] += now_ - tlast; tlast = now_; } } while (0)
+
+    auto get = [&](int i) {
+        ChildEntry e;
+        if (i < KS) {
+            const float4 v = pe4[i];
+            e.q = v.x; e.top = v.y;
+            const uint32_t u = __float_as_uint(v.z);
+            e.a = u & 255; e.id = u >> 8;
+        } else e = cl[i];
+        return e;
+    };
+    auto put = [&](int i, const ChildEntry &e) {
+        if (i < KS) pe4[i] = make_float4(e.q, e.top, __uint_as_float((uint32_t)e.a | ((uint32_t)e.id << 8)), 0.f);
+        else cl[i] = e;
+    };
+
+    // asynchronous fetch of everything a visit of node `n` needs that has a known address: its record -> entry slot 0, its
+    // row summary -> slot 1, its pi row -> the (dead) sums row.  Issued when the descent steps to the node; consumed at the
+    // next service, a trip or more later, so the DRAM latency is spent while the other lanes run their passes.
+    auto prefetch_node = [&](int n) {
+        const size_t slot = (size_t)b * T + n;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pe_addr), "l"(t.node + slot) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pe_addr + 16u), "l"(t.aux + slot) : "memory");
+        const float4 *row = reinterpret_cast<const float4 *>(t.pi + slot * t.AP);
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+            if (c < nrow4) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ps_addr + 16u * c), "l"(row + c) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
     while (true) {
-        // ---- A: finished descents write their result and take the next env -------------------------------------------
-        bl_node nd;
-        bool evaluable = false, fresh = false;
-        if (state == ST_VISIT) {
-            if (b >= 0 && cur >= 0) { nd = bl_ld_node(t.node + (size_t)b * T + cur); evaluable = !nd.terminal; }
-            if (!evaluable) {
-                if (b >= 0) {
-                    t.leaf[b] = (int16_t)cur;                      // existing terminal child, or -1: expand_step decides
-                    t.leaf_parent[b] = (int16_t)parent;
-                    t.leaf_action[b] = (int16_t)action;
-                    c_desc++;
+        const bool pass0 = state == ST_PASS || state == ST_FINAL;
+        const unsigned livem = __ballot_sync(FULL, state != ST_IDLE), passm = __ballot_sync(FULL, pass0);
+        if (livem == 0) break;
+        tick(0);
+        const unsigned needm = livem & ~passm;
+        if (passm == 0 || __popc(needm) * BL_GATE_DEN >= __popc(livem) * BL_GATE_NUM) {
+            // ---- G: inverse-CDF search over the running sums (descend_kernel, cuda.cu:160-176) ----------------------------------
+            if (state == ST_SAMPLE) {
+                // every term is >= 0 (checked for child terms in C), so the sums are non-decreasing: first index with sum >= r.
+                // The reference additionally skips p == 0 entries: the first hit can only have p == 0 when r == 0 (then the
+                // answer is the first nonzero entry), and when no sum reaches r the answer is the last nonzero entry.
+                int l = 0;
+#pragma unroll
+                for (int step = STEP0; step; step >>= 1) {
+                    const int np = l + step;
+                    if (np <= A && ps[np - 1] < r) l = np;
                 }
-                fresh = true;
+                const int first_nz = nzpos & 255, last_nz = (nzpos >> 8) & 255;
+                action = first_nz == 255 ? -1 : (l < A ? (r <= 0.f ? first_nz : l) : last_nz);
+                state = ST_ADVANCE;
             }
-        }
-        const unsigned req = __ballot_sync(FULL, fresh);
-        if (req) {
-            int base = t.B;
-            if (!exhausted) {
-                if (lane == 0) base = atomicAdd(queue, __popc(req));
-                base = __shfl_sync(FULL, base, 0);
-                exhausted = base + __popc(req) >= t.B;
+            // ---- H: step to the chosen child; its data starts travelling now ----------------------------------------------------
+            if (state == ST_ADVANCE) {
+                parent = cur;
+                int next = -1;
+                for (int i = 0; i < nc; i++) {
+                    const ChildEntry e = get(i);
+                    if (e.a == action) next = e.id;
+                }
+                cur = action >= 0 ? next : -1;
+                state = ST_VISIT;
+                if (cur >= 0) prefetch_node(cur);
             }
-            if (fresh) {
-                const int nb = base + __popc(req & ((1u << lane) - 1u));
-                b = nb < t.B ? nb : -1;
-                cur = 0; parent = 0; action = -1;
-                state = b < 0 ? ST_IDLE : ST_VISIT;
-                if (b >= 0) { nd = bl_ld_node(t.node + (size_t)b * T); evaluable = !nd.terminal; }   // a terminal root ends the descent next trip
+            tick(1);
+            // ---- A: finished descents write their result and take the next env -------------------------------------------
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            bl_node nd;
+            bool evaluable = false, fresh = false;
+            if (state == ST_VISIT) {
+                if (b >= 0 && cur >= 0) { union { float4 f; bl_node n; } x; x.f = pe4[0]; nd = x.n; evaluable = !nd.terminal; }
+                if (!evaluable) {
+                    if (b >= 0) {
+                        t.leaf[b] = (int16_t)cur;                      // existing terminal child, or -1: expand_step decides
+                        t.leaf_parent[b] = (int16_t)parent;
+                        t.leaf_action[b] = (int16_t)action;
+                        c_desc++;
+                    }
+                    fresh = true;
+                }
             }
-        }
-        if (__all_sync(FULL, state == ST_IDLE)) break;
-
-        // ---- B: visit — child list, N, lambda, random number, row -> registers --------------------------------------------
-        if (state == ST_VISIT && evaluable) {
-            const size_t node0 = (size_t)b * T;
-            const int seat = nd.seat;
-            int N = 0;
-            nc = 0;
-            cmask = 0;
-            for (int c = nd.first_child; c >= 0;) {
-                const bl_node ch = bl_ld_node(t.node + node0 + c);
-                const ChildEntry e = {qn(ch.w[seat], ch.n), 0.f, (int)ch.relation, c};
-                if (nc == 0) e0 = e; else if (nc == 1) e1 = e; else cl[nc] = e;
-                cmask |= 1ull << (ch.relation >> 2);
-                N += ch.n;
-                nc++;
-                c = ch.next_sib;
+            const unsigned req = __ballot_sync(FULL, fresh);
+            if (req) {
+                int base = t.B;
+                if (!exhausted && !all_resident) {
+                    if (lane == 0) base = atomicAdd(queue, __popc(req));
+                    base = __shfl_sync(FULL, base, 0);
+                    exhausted = base + __popc(req) >= t.B;
+                }
+                if (fresh) {
+                    int nb = base + __popc(req & ((1u << lane) - 1u));
+                    if (all_resident) nb = (b < 0 && !exhausted) ? (int)blockIdx.x * 32 + lane : t.B;
+                    b = nb < t.B ? nb : -1;
+                    cur = 0; parent = 0; action = -1;
+                    state = b < 0 ? ST_IDLE : ST_VISIT;
+                    if (b >= 0) prefetch_node(0);
+                }
+                if (all_resident) exhausted = true;
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                // a terminal root ends the descent at the next service
+                if (fresh && b >= 0) { union { float4 f; bl_node n; } x; x.f = pe4[0]; nd = x.n; evaluable = !nd.terminal; }
             }
-            N += A - nc;                                        // every child-less action counts 1 (cuda.cu:91)
-            const float lambda = bl_lambda(bl_h2f(t.c_puct[b]), N, A);
-            if (rands) r = bl_h2f(rands[node0 + cur]);
-            else r = bl_uniform_half_grid(bl_philox(seed ^ (move * 0x9E3779B97F4A7C15ull), (uint64_t)b,
-                                                    ((uint64_t)sim << 32) | (uint32_t)cur).x);
-            const bl_aux ax = bl_ld_aux(t.aux + node0 + cur);
-            nzpos = (uint32_t)ax.first_nz | ((uint32_t)ax.last_nz << 8);
-            // row: top = lambda*pi, staged in the lane's shared-memory row
-            const float4 *row = reinterpret_cast<const float4 *>(t.pi + (node0 + cur) * t.AP);
+            tick(2);
+            // ---- B: visit — row into registers, child list, N, lambda, random number ------------------------------------------
+            if (state == ST_VISIT && evaluable) {
+                const size_t node0 = (size_t)b * T;
+                const int seat = nd.seat;
+                bl_aux ax;
+                { union { float4 f; bl_aux a; } x; x.f = pe4[1]; ax = x.a; }
+                const float c_puct = bl_h2f(t.c_puct[b]);
+                if (rands) r = bl_h2f(rands[node0 + cur]);
+                else r = bl_uniform_half_grid(bl_philox(seed ^ (move * 0x9E3779B97F4A7C15ull), (uint64_t)b,
+                                                        ((uint64_t)sim << 32) | (uint32_t)cur).x);
+                int N = 0;
+                nc = 0;
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < nrow4) v = row[c];
-                ps4[c] = make_float4(__fmul_rn(lambda, v.x), __fmul_rn(lambda, v.y), __fmul_rn(lambda, v.z), __fmul_rn(lambda, v.w));
-            }
-            // alpha seed (newton_search, cuda.cu:44-50): max_a (q[a] + max(lambda*pi[a], 1e-4)); rounding is monotone, so the
-            // child-less part is max(RN(lambda*max_pi), 1e-4); tiny-value test on the smallest nonzero entry (conservative)
-            float alpha0 = fmaxf(__fmul_rn(lambda, ax.max_pi), 1.e-4f);
-            const float tmin = __fmul_rn(lambda, bl_minnz(ax));
-            const bool tiny = tmin < BL_TINY;
-            auto adopt = [&](ChildEntry &e) {
-                const float tv = ps[e.a];
-                e.top = tv;
-                alpha0 = fmaxf(alpha0, __fadd_rn(e.q, fmaxf(tv, 1.e-4f)));
-                ps[e.a] = -tv;                                  // sign = "has a child"; the numerator stays in the entry
-            };
-            if (nc > 0) adopt(e0);
-            if (nc > 1) adopt(e1);
-            for (int i = 2; i < nc; i++) { ChildEntry e = cl[i]; adopt(e); cl[i] = e; }
+                for (int w = 0; w < NW; w++) cm[w] = 0;
+                auto adopt = [&](const bl_node &ch, int id) {
+                    const int a = ch.relation;
+                    put(nc, ChildEntry{qn.fast(seat ? ch.w[1] : ch.w[0], ch.n), ps[a], a, id});      // top: pi for now, scaled below
+                    const u64 bit = 1ull << (a & 63);
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                const float4 v = ps4[c];
-                tp[2 * c] = pk(v.x, v.y); tp[2 * c + 1] = pk(v.z, v.w);
+                    for (int w = 0; w < NW; w++) cm[w] |= ((a >> 6) == w) ? bit : 0ull;    // (kept in registers: no indexed access)
+                    N += ch.n;
+                    nc++;
+                };
+                if (scan_ok) {
+                    // children = the nodes whose parent is `cur`: one scan of the env's parent row (independent 16-byte loads)
+                    // instead of a walk down the sibling list (one dependent load per child); their records are then fetched
+                    // together by cp.async straight into the lane's entry slots
+                    const uint4 *prow = reinterpret_cast<const uint4 *>(t.parent_of + (size_t)b * TP);
+                    const uint32_t cur2 = (uint32_t)cur * 0x10001u;
+                    u64 mm[MW];
+#pragma unroll
+                    for (int w = 0; w < MW; w++) {
+                        u64 m64 = 0;
+                        if (w * 8 < nscan) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                if (w * 8 + j < nscan) {
+                                    const uint4 pv = bl_ld16_hint(prow + w * 8 + j, keep);
+                                    const uint32_t e0 = __vcmpeq2(pv.x, cur2), e1 = __vcmpeq2(pv.y, cur2), e2 = __vcmpeq2(pv.z, cur2),
+                                                   e3 = __vcmpeq2(pv.w, cur2);
+                                    const uint32_t m8 = ((e0 & 1u) | ((e0 >> 15) & 2u)) | (((e1 & 1u) | ((e1 >> 15) & 2u)) << 2) |
+                                                        (((e2 & 1u) | ((e2 >> 15) & 2u)) << 4) | (((e3 & 1u) | ((e3 >> 15) & 2u)) << 6);
+                                    m64 |= (u64)m8 << (8 * j);
+                                }
+                            }
+                        }
+                        mm[w] = m64;
+                    }
+                    tick(7);
+                    int k = 0;
+#pragma unroll
+                    for (int w = 0; w < MW; w++)
+                        for (u64 m = mm[w]; m; m &= m - 1) {
+                            const int id = w * 64 + __ffsll((long long)m) - 1;
+                            if (k < KS)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pe_addr + 16u * k), "l"(t.node + node0 + id) : "memory");
+                            k++;
+                        }
+                    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                    tick(8);
+                    k = 0;
+#pragma unroll
+                    for (int w = 0; w < MW; w++)
+                        for (u64 m = mm[w]; m; m &= m - 1) {
+                            const int id = w * 64 + __ffsll((long long)m) - 1;
+                            bl_node ch;
+                            if (k < KS) { union { float4 f; bl_node n; } x; x.f = pe4[k]; ch = x.n; }
+                            else ch = bl_ld_node_hint(t.node + node0 + id, keep);
+                            adopt(ch, id);
+                            k++;
+                        }
+                } else {
+                    for (int c = nd.first_child; c >= 0;) {
+                        const bl_node ch = bl_ld_node_hint(t.node + node0 + c, keep);
+                        adopt(ch, c);
+                        c = ch.next_sib;
+                    }
+                }
+                tick(9);
+                N += A - nc;                                        // every child-less action counts 1 (cuda.cu:91)
+                const float lambda = bl_lambda(c_puct, N, A);
+                nzpos = (uint32_t)ax.first_nz | ((uint32_t)ax.last_nz << 8);
+                const u64 lam2 = pk(lambda, lambda);
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {                   // top = lambda*pi, from the landed row
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < nrow4) v = ps4[c];
+                    tp[2 * c] = mul2(pk(v.x, v.y), lam2); tp[2 * c + 1] = mul2(pk(v.z, v.w), lam2);
+                }
+                tick(10);
+                // alpha seed (newton_search, cuda.cu:44-50): max_a (q[a] + max(lambda*pi[a], 1e-4)); rounding is monotone, so the
+                // child-less part is max(RN(lambda*max_pi), 1e-4); tiny-value test on the smallest nonzero entry (conservative)
+                float alpha0 = fmaxf(__fmul_rn(lambda, ax.max_pi), 1.e-4f);
+                const bool tiny = __fmul_rn(lambda, bl_minnz(ax)) < BL_TINY;
+                for (int i = 0; i < nc; i++) {
+                    ChildEntry e = get(i);
+                    e.top = __fmul_rn(lambda, e.top);
+                    alpha0 = fmaxf(alpha0, __fadd_rn(e.q, fmaxf(e.top, 1.e-4f)));
+                    put(i, e);
+                }
+                alpha = alpha0; it = 0; error = BL_INF;
+                state = tiny ? ST_SLOW : ST_PASS;
+                c_evals++; c_children += nc;
             }
-            alpha = alpha0; it = 0; error = BL_INF;
-            state = tiny ? ST_SLOW : ST_PASS;
-            c_evals++; c_children += nc;
         }
 
+        tick(3);
         // ---- C: child terms of this pass (full divisions), parked at their positions ----------------------------------------
-        const bool pass = state == ST_PASS || state == ST_FINAL;
-        if (pass) {
+        if (state == ST_PASS || state == ST_FINAL) {
             bool bad = false;
-            auto park = [&](const ChildEntry &e) {
-                const float bot = __fsub_rn(alpha, e.q);
-                const float s = __fdiv_rn(e.top, bot);
+            for (int i = 0; i < nc; i++) {
+                const ChildEntry e = get(i);
+                const float bot = __fsub_rn(alpha, e.q), bb = __fmul_rn(bot, bot);
+                const float s = bl_div_fast(e.top, bot), g = bl_div_fast(-e.top, bb);
                 ps[e.a] = s;
-                pg[e.a] = __fdiv_rn(-e.top, __fmul_rn(bot, bot));
-                bad |= !(s >= 0.f && s <= 3.0e38f);              // negative / non-finite term: the prefix would not be monotone
-            };
-            if (nc > 0) park(e0);
-            if (nc > 1) park(e1);
-            for (int i = 2; i < nc; i++) park(cl[i]);
+                pg[e.a] = g;
+                // bot outside [2^-60, 2^60] (never seen; alpha > q by construction) leaves the branch-free division's safe range;
+                // a negative / non-finite term would also break the monotone running sums: both go to the exact serial path
+                bad |= !(bot >= 8.67e-19f && bot <= 1.15e18f) || !(s >= 0.f && s <= 3.0e38f);
+            }
             if (bad) state = ST_SLOW;
         }
         // ---- D: exact serial fallback: the reference loops verbatim ---------------------------------------------------------
         if (state == ST_SLOW) {
 #pragma unroll
             for (int c = 0; c < NCH; c++) ps4[c] = make_float4(lo(tp[2 * c]), hi(tp[2 * c]), lo(tp[2 * c + 1]), hi(tp[2 * c + 1]));
-            auto topf = [&](int a) { return fabsf(ps[a]); };
+            auto topf = [&](int a) { return ps[a]; };
             auto qf = [&](int a) {
                 float q = 0.f;
-                if (nc > 0 && e0.a == a) q = e0.q;
-                if (nc > 1 && e1.a == a) q = e1.q;
-                for (int i = 2; i < nc; i++) if (cl[i].a == a) q = cl[i].q;
+                for (int i = 0; i < nc; i++) { const ChildEntry e = get(i); if (e.a == a) q = e.q; }
                 return q;
             };
             int iters;
@@ -194,24 +335,26 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
             state = ST_ADVANCE;
         }
         asm volatile("" ::: "memory");
+        tick(4);
 
         // ---- E: one Newton pass: the two sequential sums ----------------------------------------------------------------------
-        const bool pass2 = state == ST_PASS || state == ST_FINAL;
+        const bool pass = state == ST_PASS || state == ST_FINAL;
         float accS = 0.f, accG = 0.f;
-        if (__any_sync(FULL, pass2)) {
+        if (__any_sync(FULL, pass)) {
             const float bS = alpha, bG = __fmul_rn(alpha, alpha);
-            const float yS = __frcp_rn(bS), yG = -__frcp_rn(bG);     // g terms: divide lambda*pi by -(alpha^2)
+            const float yS = bl_rcp_fast(bS), yG = -bl_rcp_fast(bG); // g terms: divide lambda*pi by -(alpha^2); alpha in [1e-4, ~c_puct+1]
             const u64 yS2 = pk(yS, yS), yG2 = pk(yG, yG), nbS2 = pk(-bS, -bS), bG2 = pk(bG, bG);
             float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
-                const uint32_t has = (uint32_t)(cmask >> c) & 1u;
+                // which of the chunk's 4 actions have a child (none for a lane that is not in a pass: its rows may be in flight)
+                const uint32_t kids = pass ? (uint32_t)(cm[(4 * c) >> 6] >> ((4 * c) & 63)) & 15u : 0u;
                 asm volatile(
                     "{\n.reg .pred p;\nsetp.ne.u32 p, %8, 0;\n"
                     "@p ld.shared.v4.f32 {%0,%1,%2,%3}, [%9];\n"
                     "@p ld.shared.v4.f32 {%4,%5,%6,%7}, [%10];\n}"
                     : "+f"(p0), "+f"(p1), "+f"(p2), "+f"(p3), "+f"(g0), "+f"(g1), "+f"(g2), "+f"(g3)
-                    : "r"(has), "r"(ps_addr + 16u * c), "r"(pg_addr + 16u * c));
+                    : "r"(kids), "r"(ps_addr + 16u * c), "r"(pg_addr + 16u * c));
                 const u64 t01 = tp[2 * c], t23 = tp[2 * c + 1];
                 u64 q = mul2(t01, yS2), rr = fma2(nbS2, q, t01);
                 const u64 s01 = fma2(rr, yS2, q);
@@ -221,17 +364,17 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                 const u64 s23 = fma2(rr, yS2, q);
                 q = mul2(t23, yG2); rr = fma2(bG2, q, t23);
                 const u64 h23 = fma2(rr, yG2, q);
-                const bool c0 = (int)(unsigned)t01 < 0, c1 = (int)(unsigned)(t01 >> 32) < 0;
-                const bool c2 = (int)(unsigned)t23 < 0, c3 = (int)(unsigned)(t23 >> 32) < 0;
+                const bool c0 = kids & 1u, c1 = kids & 2u, c2 = kids & 4u, c3 = kids & 8u;
                 accS = __fadd_rn(accS, c0 ? p0 : lo(s01)); accG = __fadd_rn(accG, c0 ? g0 : lo(h01)); const float o0 = accS;
                 accS = __fadd_rn(accS, c1 ? p1 : hi(s01)); accG = __fadd_rn(accG, c1 ? g1 : hi(h01)); const float o1 = accS;
                 accS = __fadd_rn(accS, c2 ? p2 : lo(s23)); accG = __fadd_rn(accG, c2 ? g2 : lo(h23)); const float o2 = accS;
                 accS = __fadd_rn(accS, c3 ? p3 : hi(s23)); accG = __fadd_rn(accG, c3 ? g3 : hi(h23)); const float o3 = accS;
-                ps4[c] = make_float4(o0, o1, o2, o3);              // harmless for lanes that are not in a pass: their row is dead
+                if (pass) ps4[c] = make_float4(o0, o1, o2, o3);    // a lane waiting for its visit must not touch the row
             }
         }
+        tick(5);
         // ---- F: Newton update (newton_search, cuda.cu:57-66) ---------------------------------------------------------------
-        if (pass2) {
+        if (pass) {
             if (state == ST_PASS) {
                 it++;
                 c_iters++;
@@ -246,36 +389,18 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                 state = ST_SAMPLE;
             }
         }
-        // ---- G: inverse-CDF search over the running sums (descend_kernel, cuda.cu:160-176) ----------------------------------
-        if (state == ST_SAMPLE) {
-            // every term is >= 0 (checked for child terms above), so the sums are non-decreasing: first index with sum >= r.
-            // The reference additionally skips p == 0 entries: the first hit can only have p == 0 when r == 0 (then the
-            // answer is the first nonzero entry), and when no sum reaches r the answer is the last nonzero entry.
-            int l = 0, h = A;
-            while (l < h) {
-                const int mid = (l + h) >> 1;
-                if (ps[mid] >= r) h = mid; else l = mid + 1;
-            }
-            const int first_nz = nzpos & 255, last_nz = (nzpos >> 8) & 255;
-            action = first_nz == 255 ? -1 : (l < A ? (r <= 0.f ? first_nz : l) : last_nz);
-            state = ST_ADVANCE;
-        }
-        // ---- H: step to the chosen child -------------------------------------------------------------------------------------
-        if (state == ST_ADVANCE) {
-            parent = cur;
-            int next = -1;
-            if (nc > 0 && e0.a == action) next = e0.id;
-            if (nc > 1 && e1.a == action) next = e1.id;
-            for (int i = 2; i < nc; i++)
-                if (cl[i].a == action) next = cl[i].id;
-            cur = action >= 0 ? next : -1;
-            state = ST_VISIT;
-        }
+    }
+    if (PROF && lane == 0) {
+        tick(6);
+#pragma unroll
+        for (int k = 0; k < (PROF ? 12 : 1); k++) atomicAdd(prof + k, (unsigned long long)pc[k]);
+        atomicAdd(prof + 15, 1ull);
     }
     bl_count(t.counters, C_EVALS, c_evals);
     bl_count(t.counters, C_CHILDREN, c_children);
     bl_count(t.counters, C_ITERS, c_iters);
     bl_count(t.counters, C_DESCENTS, c_desc);
+#undef tick
 }
 
 // ---- expand + env step (boardlaw/mcts/__init__.py:117-129), one lane per env ---------------------------------------------------
@@ -304,6 +429,7 @@ __global__ void __launch_bounds__(XNT) expand_step_kernel(bl_tree t, int sim) {
                 ln.parent = (int16_t)parent; ln.relation = (int16_t)action; ln.first_child = -1; ln.next_sib = pn.first_child;
                 ln.n = 0; ln.w[0] = 0; ln.w[1] = 0;
                 t.node[node0 + parent].first_child = (int16_t)sim;
+                t.parent_of[(size_t)b * ((T + 7) & ~7) + sim] = (int16_t)parent;
             } else {                                            // stopped at an existing terminal child: reuse its slot
                 ln = bl_ld_node(t.node + node0 + leaf);
             }
@@ -350,7 +476,7 @@ __global__ void __launch_bounds__(256) divtest_kernel(uint64_t seed, int n_div, 
     for (int i = blockIdx.x; i < n_div; i += gridDim.x) {
         bl_philox_out o = bl_philox(seed, (uint64_t)i, 1);
         unsigned mant = (i & 7) == 0 ? 0x7FFFFFu : ((i & 7) == 1 ? 0u : (o.x & 0x7FFFFFu));
-        int ex = 127 - 27 + (int)(o.y % 30);                                   // 2^-27 .. 2^2
+        int ex = 127 - 27 + (int)(o.y % 44);                                   // 2^-27 .. 2^16
         float bdiv = __uint_as_float(((unsigned)ex << 23) | mant);
         float y = __frcp_rn(bdiv);
         const u64 y2 = pk(y, -y), nb2 = pk(-bdiv, bdiv);
@@ -367,29 +493,41 @@ __global__ void __launch_bounds__(256) divtest_kernel(uint64_t seed, int n_div, 
             const u64 d = fma2(rr, y2, q);
             bad += (__float_as_uint(lo(d)) != __float_as_uint(__fdiv_rn(num, bdiv)));
             bad += (__float_as_uint(hi(d)) != __float_as_uint(__fdiv_rn(-num, bdiv)));
+            // branch-free reciprocal / quotient (mcts_core.cuh), also with q-normalisation-like operands (any sign, zero, up to 2^15)
+            bad += (__float_as_uint(bl_rcp_fast(bdiv)) != __float_as_uint(y));
+            bad += (__float_as_uint(bl_div_fast(-num, bdiv)) != __float_as_uint(__fdiv_rn(-num, bdiv)));
+            const float big = __uint_as_float(((unsigned)(127 - 30 + (int)(p.w % 46)) << 23) | nm | ((p.z & 1u) << 31));   // 2^-30 .. 2^15
+            bad += (__float_as_uint(bl_div_fast(big, bdiv)) != __float_as_uint(__fdiv_rn(big, bdiv)));
+            bad += (__float_as_uint(bl_div_fast(0.f, bdiv)) != __float_as_uint(__fdiv_rn(0.f, bdiv)));
         }
     }
     if (bad) atomicAdd(mismatch, bad);
 }
 
-template <int NCH>
-int launch_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, int cap, cudaStream_t st) {
-    const size_t smem = (size_t)2 * 32 * 4 * NCH * sizeof(float);
+unsigned long long *g_phase_prof = nullptr;
+
+template <int NCH, bool PROF>
+int launch_v3p(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, int cap, cudaStream_t st) {
+    const size_t smem = (size_t)3 * 32 * 4 * NCH * sizeof(float);
     static int occ = 0;
     if (occ == 0) {
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(descend_v3_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(descend_v3_kernel<NCH, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
         }
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, descend_v3_kernel<NCH>, 32, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, descend_v3_kernel<NCH, PROF>, 32, smem);
         if (e != cudaSuccess) return (int)e;
         if (occ < 1) { occ = 0; return -2; }
     }
     const int need = (t->B + 31) / 32;
     const int grid = need < occ * BL_NUM_SMS ? need : occ * BL_NUM_SMS;
     if ((int64_t)grid * 32 * cap * (int64_t)sizeof(ChildEntry) > t->scratch_bytes) return -3;
-    descend_v3_kernel<NCH><<<grid, 32, smem, st>>>(*t, sim, rands, seed, reinterpret_cast<ChildEntry *>(t->scratch), cap);
+    descend_v3_kernel<NCH, PROF><<<grid, 32, smem, st>>>(*t, sim, rands, seed, reinterpret_cast<ChildEntry *>(t->scratch), cap, g_phase_prof);
     return (int)cudaGetLastError();
+}
+template <int NCH>
+int launch_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, int cap, cudaStream_t st) {
+    return g_phase_prof ? launch_v3p<NCH, true>(t, sim, rands, seed, cap, st) : launch_v3p<NCH, false>(t, sim, rands, seed, cap, st);
 }
 
 int child_cap(const bl_tree *t) { return t->A < t->T - 1 ? t->A : (t->T > 1 ? t->T - 1 : 1); }
@@ -426,6 +564,11 @@ int bl_descend_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed
     else rc = -2;
     if (rc) return rc;
     return bl_expand_step(t, sim, st);
+}
+
+extern "C" int bl_debug_set_phase_profile(uint64_t *buf) {
+    g_phase_prof = reinterpret_cast<unsigned long long *>(buf);
+    return 0;
 }
 
 extern "C" int bl_selftest_division(uint64_t seed, int n_div, int n_num, uint64_t *mismatch, bl_stream stream) {

@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(256) reset_kernel(bl_tree t, const uint8_t *__
         long long b = i / t.A; int c = (int)(i - b * t.A);
         t.board[(b * t.T) * t.BP + c] = board[i];
     }
+    const int TP = (t.T + 7) & ~7;
+    for (long long i = i0; i < (long long)t.B * TP; i += stride) t.parent_of[i] = -1;
     for (long long i = i0; i < t.B; i += stride) t.c_puct[i] = c_puct;
     int *qr = reinterpret_cast<int *>(t.qrange);
     for (long long i = i0; i <= t.T; i += stride) {
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
             int N = 0, nc = 0;
             for (int c = nd.first_child; c >= 0;) {
                 const bl_node ch = bl_ld_node(t.node + node0 + c);
-                q[ch.relation * FP] = qn(ch.w[seat], ch.n);
+                q[ch.relation * FP] = qn(seat ? ch.w[1] : ch.w[0], ch.n);
                 N += ch.n;
                 nc++;
                 c = ch.next_sib;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(ENT) root_kernel(bl_tree t, int sim, const bl_
     int N = 0, nc = 0;
     for (int c = root.first_child; c >= 0;) {
         const bl_node ch = bl_ld_node(t.node + node0 + c);
-        q[ch.relation * FP] = qn(ch.w[seat], ch.n);
+        q[ch.relation * FP] = qn(seat ? ch.w[1] : ch.w[0], ch.n);
         N += ch.n;
         nc++;
         c = ch.next_sib;

@@ -29,6 +29,29 @@ __device__ __forceinline__ void bl_st_node_stats(bl_node *p, const bl_node &n) {
     x.n = n;
     reinterpret_cast<uint2 *>(p)[1] = make_uint2(x.u.z, x.u.w);
 }
+// L2 residency: the 32 bytes of node/aux records per (env, node) are re-read on every simulation and fit in the 126 MB L2
+// (c2: 64 MB), the pi rows and boards stream through it; record accesses carry an evict_last policy.
+__device__ __forceinline__ uint64_t bl_policy_keep() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 bl_ld16_hint(const void *p, uint64_t pol) {
+    uint4 v;
+    asm("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+// read-only use (descent): the records are not written by the kernel that calls these
+__device__ __forceinline__ bl_node bl_ld_node_hint(const bl_node *p, uint64_t pol) {
+    union { uint4 u; bl_node n; } x;
+    x.u = bl_ld16_hint(p, pol);
+    return x.n;
+}
+__device__ __forceinline__ bl_aux bl_ld_aux_hint(const bl_aux *p, uint64_t pol) {
+    union { uint4 u; bl_aux a; } x;
+    x.u = bl_ld16_hint(p, pol);
+    return x.a;
+}
 __device__ __forceinline__ float bl_minnz(const bl_aux &a) { return __uint_as_float((uint32_t)a.minnz_hi << 16); }
 
 // descend.cu: task-parallel descent (writes t.leaf = existing terminal child or -1, t.leaf_parent, t.leaf_action)

@@ -1,8 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 timeout 1700 python -m pytest tests -m gpu -q --maxfail=40 --no-header -rN --tb=short 2>&1 | tail -150 > gpurun_out/pytest_gpu.log
 grep -E "passed|failed" gpurun_out/pytest_gpu.log | tail -3
 grep -E "^(FAILED|ERROR)|^E  .*Error|^_{5,}" gpurun_out/pytest_gpu.log | cut -c1-200 | head -40
-timeout 600 python bench.py --config c2 --steps 3 --warmup 3 > gpurun_out/bench_c2.log 2>&1
-tail -c 3500 gpurun_out/bench_c2.log
+timeout 600 python tools/descend_phases.py c2 > gpurun_out/phases.log 2>&1
+tail -16 gpurun_out/phases.log
+timeout 600 python bench.py --config c2 --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_c2.log 2>&1
+tail -c 3500 gpurun_out/bench_c2.log | grep -o '"value": [0-9.]*\|"ms_per_move_by_kernel": {[^}]*}' | head -3

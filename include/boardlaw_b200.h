@@ -176,6 +176,8 @@ typedef struct bl_tree {
     uint8_t *board;       /* (B,T,BP) u8 absolute-frame boards                                      */
     bl_node *node;        /* (B,T)                                                                  */
     bl_aux *aux;          /* (B,T)                                                                  */
+    int16_t *parent_of;   /* (B,TP) i16, TP = T rounded up to a multiple of 8: parent of every node (-1 = none) as one
+                             contiguous row per env — the descent finds a node's children by scanning it             */
     bl_half *c_puct;      /* (B,)   half                                                            */
     int16_t *leaf;        /* (B,)   i16 leaf of the current simulation                              */
     int16_t *leaf_parent; /* (B,)   i16                                                             */
@@ -213,6 +215,11 @@ int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint
  * 1 = one lane per env in lock step, reference loops verbatim (engine.cu; kept as an on-device cross-check).
  * Both produce identical results. */
 int bl_debug_set_descend_variant(int variant);
+
+/* Phase clock of the descent kernel: when `buf` (16 x uint64 on the device, zeroed by the caller) is non-NULL every warp adds the
+ * cycles it spent per phase — [0] loop head, [1] sample+advance, [2] finish/fetch, [3] visit, [4] child terms, [5] pass,
+ * [6] Newton update/tail, [7..10] visit sub-phases — and [15] += 1.  NULL (default) switches it off. */
+int bl_debug_set_phase_profile(uint64_t *buf);
 
 /* Self test: counts operand pairs for which the shared-reciprocal division of descend.cu differs from the IEEE
  * division (expected 0) over n_div x n_num pseudo-random pairs drawn from the descent's operand ranges. */
