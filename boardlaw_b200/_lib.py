@@ -48,6 +48,7 @@ SIGNATURES = {
     'bl_mcts_root': (c_int, [P] * 10 + [c_int] * 4 + [P]),
     'bl_mcts_backup': (c_int, [P] * 7 + [c_int] * 3 + [P]),
     'bl_mcts_transition_q': (c_int, [P] * 4 + [c_int] * 3 + [P]),
+    'bl_fc_uses_tensor_cores': (c_int, [POINTER(FCParams)]),
     'bl_fc_scratch_bytes': (c_int64, [POINTER(FCParams), c_int]),
     'bl_fc_forward': (c_int, [POINTER(FCParams), P, P, P, P, P, c_int, P]),
     'bl_tree_scratch_bytes': (c_int64, [POINTER(Tree)]),

@@ -322,6 +322,12 @@ __global__ void __launch_bounds__(256) gather_leaves_kernel(bl_tree t, int node,
     }
 }
 
+}  // namespace
+// net_tc.cu
+int bl_fc_forward_tc_tree(const bl_fc_params *p, const bl_tree *t, cudaStream_t st);
+bool bl_fc_tc_supported(const bl_fc_params *p);
+namespace {
+
 int grid1d(long long n, int block) {
     long long g = (n + block - 1) / block, cap = (long long)BL_NUM_SMS * 16;
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
@@ -411,6 +417,8 @@ extern "C" int bl_tree_eval_leaves(const bl_tree *t, const bl_fc_params *p, int 
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     (void)sim;
+    // tensor-core path: one kernel reads the leaf boards from the tree and writes pi rows / summaries / values back into it
+    if (bl_fc_tc_supported(p)) return bl_fc_forward_tc_tree(p, t, bl_cu(stream));
     EvalScratch s = split_scratch(t, scratch);
     gather_leaves_kernel<<<grid1d((long long)t->B * t->A, 256), 256, 0, bl_cu(stream)>>>(*t, -1, s.board, s.seats);
     int e = bl_fc_forward(p, s.board, s.seats, s.logits, s.v, s.net, t->B, stream);

@@ -141,6 +141,8 @@ int bl_fc_forward_tc(const bl_fc_params *p, const uint8_t *board, long long boar
                      float *v, int B, cudaStream_t st);
 bool bl_fc_tc_supported(const bl_fc_params *p);
 
+extern "C" int bl_fc_uses_tensor_cores(const bl_fc_params *p) { return bl_fc_tc_supported(p) ? 1 : 0; }
+
 extern "C" int64_t bl_fc_scratch_bytes(const bl_fc_params *p, int B) {
     return (int64_t)sizeof(float) * B * (2 * (int64_t)p->W + (int64_t)p->S * p->S);
 }

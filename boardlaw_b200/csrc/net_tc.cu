@@ -1,23 +1,31 @@
 // Tensor-core policy/value network forward for sm_100a: the whole FCModel (boardlaw/networks.py:20-41) for a tile of
-// 128 envs in ONE kernel — tcgen05.mma with TMEM accumulators, weights streamed by the TMA engine (cp.async.bulk),
-// activations never leaving the SM.
+// 128 envs in ONE kernel — tcgen05.mma with both the accumulator AND the activation operand in tensor memory, weights
+// streamed by the TMA engine (cp.async.bulk) through an mbarrier ring; activations never touch shared or global memory.
 //
-//   layer 0     x  = obs . W_in^T + b_in                 (obs generated from the board bytes, exact in fp16)
-//   layer 1..D  x += alpha_k (relu(x) . W_k^T + b_k)     (ReZero residual, boardlaw/networks.py:10-18)
-//   heads       [policy | value] = x . [W_p ; w_v]^T      -> masked log-softmax (heads.py:101-104), tanh (heads.py:136-142)
+//   layer 0     z  = obs . W_in^T                        (obs generated from the board bytes, exact in fp16)      c_0 = b_in
+//   layer 1..D  z += relu(z + c_{k-1}) . (alpha_k W_k)^T   (ReZero residual, boardlaw/networks.py:10-18; the MMA accumulates IN PLACE on z)
+//                                                          c_k = c_{k-1} + alpha_k b_k   (biases never enter the accumulator)
+//   heads       [policy | value] = (z + c_D) . [W_p ; w_v]^T -> masked log-softmax (heads.py:101-104), tanh (heads.py:136-142)
 //
 // fp32 accuracy on fp16 tensor cores: every fp32 operand is split x = hi + lo with hi = fp16(x), lo = fp16(x - hi)
 // (22 significand bits), and a product is accumulated as hi*hi + hi*lo + lo*hi in fp32 (the dropped lo*lo term is
-// 2^-22 relative).  Three tcgen05.mma per K-step instead of one; measured error vs the fp32 reference ~1e-6
-// (tests/test_gpu_net.py, tolerance 1e-5).  precision=1 issues only hi*hi (the reference's autocast precision class).
+// 2^-22 relative): three tcgen05.mma per K-step.  Measured error vs the fp32 reference ~1e-6 (tests/test_gpu_net.py,
+// tolerance 1e-5).  precision=1 issues only hi*hi (the reference's autocast precision class).
+//
+// Tensor memory (512 columns x 128 lanes, lane = env row of the tile):
+//   [0,256)   z, fp32 (the heads' accumulator re-uses it once z is dead)
+//   [256,384) activation operand, hi halves, two K elements per column (A of tcgen05.mma in "TS" form)
+//   [384,512) activation operand, lo halves (layer 0's one-hot operand has no lo part and may use both regions)
 //
 // Per-CTA roles (320 threads, 1 CTA/SM, persistent over tiles):
-//   warps 0-7  epilogue: TMEM -> registers, bias / ReZero / relu, split to fp16, write the next layer's A operand into
-//              shared memory in the UMMA canonical K-major (no-swizzle) layout; residual stream x kept in TMEM cols 256+
+//   warps 0-7  epilogue: tcgen05.ld z -> + c -> relu -> split -> tcgen05.st the next layer's operand; heads; tree I/O
 //   warp 8     weight loader: one elected thread, cp.async.bulk of host-prepacked operand tiles into a smem ring
-//   warp 9     MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256, K=16), tcgen05.commit
-// Synchronisation is mbarrier-only between roles (full/empty ring, a_ready, acc_full).
-#include "common.cuh"
+//   warp 9     MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=128 per half, K=16)
+// The layer's N is split in two halves and its K in two halves, issued as (h0,K0) (h1,K0) (h0,K1) (h1,K1): the epilogue of
+// half 0 runs under the MMAs of (h1,K1), the epilogue of half 1 under the next layer's (h0,K0) — the tensor pipe never
+// waits for the epilogue as long as a half-epilogue is shorter than a quarter-layer of MMAs.
+// Synchronisation is mbarrier-only between roles (weight ring full/empty, a_ready[2], acc_full[2]).
+#include "engine_internal.cuh"
 #include "hex_core.cuh"
 
 namespace {
@@ -27,17 +35,19 @@ constexpr int KC = 32;                     // K elements per weight stage
 constexpr int EPI_WARPS = 8;
 constexpr int WARP_LOAD = 8, WARP_MMA = 9;
 constexpr int TC_THREADS = 320;
-constexpr int X_COL = 256;                 // TMEM column where the residual stream lives
-constexpr int MAX_STAGES = 4;
+constexpr int AH_COL = 256, AL_COL = 384;  // TMEM columns of the activation operand (hi, lo)
+constexpr int MAX_STAGES = 8;
 
 struct TcParams {
-    const uint8_t *board;                  // env e's board at board + e*board_pitch (absolute frame, A bytes)
-    const int32_t *seats;                  // (B,)
+    const uint8_t *board;                  // env e's board at board + e*board_pitch (absolute frame, A bytes); tree mode: tree.board
+    const int32_t *seats;                  // (B,); unused in tree mode
     long long board_pitch;
-    const uint8_t *blob;                   // packed operand tiles
-    const float *b_in, *b_res, *alpha, *b_head;
-    float *logits, *v;                     // (B,A), (B,2)
+    const uint8_t *blob;                   // packed operand tiles, in consumption order
+    const float *cbias;                    // (D+1, W) cumulative biases c_k, then (Np) head bias
+    float *logits, *v;                     // (B,A), (B,2) fp32 outputs (NULL in tree mode)
     int B, S, A, W, D, K0p, Np, precision, nstages;
+    int tree_mode;                         // 1: inputs are the current leaves of `tree`, outputs go straight into the tree
+    bl_tree tree;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -67,7 +77,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -78,19 +87,19 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]^T  — activation operand in tensor memory, weight operand through a shared-memory descriptor
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-#define BL_R8(a, o) "%" #a ""
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -101,17 +110,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
-          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
-          "r"(r[30]), "r"(r[31]) : "memory");
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
 // UMMA shared-memory descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -122,38 +130,54 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-
-struct Carve {
-    uint8_t *a_hi, *a_lo, *stage0;
-    uint32_t stage_bytes;
-    uint64_t *full, *empty, *a_ready, *acc_full;
-    uint32_t *tmem_ptr;
-};
-__host__ __device__ inline size_t carve_sizes(int W, int K0p, int Np, int nstages, size_t *a_hi_b, size_t *a_lo_b, size_t *stage_b) {
-    int kmax = W > K0p ? W : K0p, nmax = W > Np ? W : Np;
-    *a_hi_b = (size_t)TILE_M * kmax * 2;
-    *a_lo_b = (size_t)TILE_M * W * 2;
-    *stage_b = (size_t)nmax * KC * 2 * 2;
-    return *a_hi_b + *a_lo_b + *stage_b * nstages + 256;
+// two floats -> packed half2 (round to nearest), low half = first argument
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(TcParams p) {
+struct Shape {              // derived sizes shared by the three roles and the host packer (networks.py mirrors them)
+    int NH, Wh, nk0, nk;    // N halves, columns per half, K chunks of layer 0 / of the residual layers and heads
+    int k0_split, k_split;  // chunks in the first K half (layer 0 / other layers)
+    uint32_t stage_bytes;
+};
+__host__ __device__ inline Shape make_shape(int W, int K0p, int Np) {
+    Shape s;
+    s.NH = W >= 64 ? 2 : 1;
+    s.Wh = W / s.NH;
+    s.nk0 = K0p / KC;
+    s.nk = W / KC;
+    s.k0_split = s.NH == 2 ? (s.nk0 + 1) / 2 : s.nk0;
+    s.k_split = s.NH == 2 ? s.nk / 2 : s.nk;
+    const int rows = s.Wh > Np ? s.Wh : Np;
+    s.stage_bytes = (uint32_t)rows * KC * 2 * 2;
+    return s;
+}
+__host__ __device__ inline int board_pitch_bytes(int A) { return 4 * (((A + 3) / 4) | 1); }   // odd number of words: conflict-free rows
+size_t smem_bytes(const Shape &s, int nstages, int A) {
+    return (size_t)s.stage_bytes * nstages + (size_t)TILE_M * board_pitch_bytes(A) + 1024;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    size_t a_hi_b, a_lo_b, stage_b;
-    carve_sizes(p.W, p.K0p, p.Np, p.nstages, &a_hi_b, &a_lo_b, &stage_b);
-    uint8_t *a_hi = smem, *a_lo = smem + a_hi_b, *stage0 = a_lo + a_lo_b;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage0 + stage_b * p.nstages);
-    uint64_t *full = bars, *empty = bars + MAX_STAGES, *a_ready = bars + 2 * MAX_STAGES, *acc_full = a_ready + 1;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 1);
+    const Shape sh = make_shape(p.W, p.K0p, p.Np);
+    const int bpitch = board_pitch_bytes(p.A);                     // board tile row pitch
+    uint8_t *stage0 = smem;
+    uint8_t *btile = stage0 + (size_t)sh.stage_bytes * p.nstages;  // [TILE_M][bpitch] boards of the tile
+    uint64_t *bars = reinterpret_cast<uint64_t *>(btile + (size_t)TILE_M * bpitch + ((16 - ((size_t)TILE_M * bpitch) % 16) % 16));
+    uint64_t *full = bars, *empty = bars + MAX_STAGES, *a_ready = bars + 2 * MAX_STAGES, *acc_full = a_ready + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 2);
+    int32_t *tseat = reinterpret_cast<int32_t *>(tmem_ptr + 2);   // [TILE_M] seat | node << 8 of the tile's rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.W, D = p.D, A = p.A, S = p.S, Np = p.Np, K0p = p.K0p;
+    const int NH = sh.NH, Wh = sh.Wh;
     const int ntiles = (p.B + TILE_M - 1) / TILE_M;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nstages; s++) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
-        mbar_init(smem_u32(a_ready), EPI_WARPS);
-        mbar_init(smem_u32(acc_full), 1);
+        for (int h = 0; h < 2; h++) { mbar_init(smem_u32(a_ready + h), EPI_WARPS); mbar_init(smem_u32(acc_full + h), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_ptr), 512);
@@ -163,18 +187,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(TcParams p) {
     const uint32_t tmem = *tmem_ptr;
 
     if (warp == WARP_LOAD) {
+        // ---- weight loader: the blob is laid out in consumption order, one chunk per stage ----------------------------------
         if (lane == 0) {
             int stage = 0;
             uint32_t ph = 0;
+            const uint32_t body_bytes = (uint32_t)Wh * KC * 2 * 2, head_bytes = (uint32_t)Np * KC * 2 * 2;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t *src = p.blob;
                 for (int L = 0; L <= D + 1; L++) {
-                    const int nch = (L == 0 ? K0p : W) / KC;
-                    const uint32_t cbytes = (uint32_t)(L == D + 1 ? Np : W) * KC * 2 * 2;
+                    const int nch = L == 0 ? sh.nk0 * NH : (L <= D ? sh.nk * NH : sh.nk);
+                    const uint32_t cbytes = L <= D ? body_bytes : head_bytes;
                     for (int c = 0; c < nch; c++) {
                         mbar_wait(smem_u32(empty + stage), ph ^ 1);
                         mbar_expect_tx(smem_u32(full + stage), cbytes);
-                        bulk_g2s(smem_u32(stage0 + stage_b * stage), src, cbytes, smem_u32(full + stage));
+                        bulk_g2s(smem_u32(stage0 + (size_t)sh.stage_bytes * stage), src, cbytes, smem_u32(full + stage));
                         src += cbytes;
                         if (++stage == p.nstages) { stage = 0; ph ^= 1; }
                     }
@@ -182,64 +208,119 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(TcParams p) {
             }
         }
     } else if (warp == WARP_MMA) {
+        // ---- MMA issuer ---------------------------------------------------------------------------------------------------------
         if (lane == 0) {
             int stage = 0;
-            uint32_t ph = 0, aph = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int L = 0; L <= D + 1; L++) {
-                    const int K = L == 0 ? K0p : W, N = L == D + 1 ? Np : W;
-                    const uint32_t idesc = make_idesc(TILE_M, N);
-                    const uint32_t sbo_a = (uint32_t)(K / 8) * 128;
-                    const bool lo_a = L > 0 && p.precision == 0, lo_b = p.precision == 0;
-                    mbar_wait(smem_u32(a_ready), aph);
-                    aph ^= 1;
-                    tc_fence_after();
-                    for (int c = 0; c < K / KC; c++) {
-                        mbar_wait(smem_u32(full + stage), ph);
-                        tc_fence_after();
-                        const uint32_t sb = smem_u32(stage0 + stage_b * stage);
+            uint32_t ph = 0, aph[2] = {0, 0};
+            const bool lo_b = p.precision == 0;
+            // one K chunk (KC = 2 K-steps of 16) of one N block: D columns [dcol, dcol+N), A columns from acol
+            auto chunk = [&](uint32_t dcol, int N, int kchunk, bool lo_a, bool fresh_acc) {
+                mbar_wait(smem_u32(full + stage), ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(stage0 + (size_t)sh.stage_bytes * stage);
+                const uint32_t idesc = make_idesc(TILE_M, N);
 #pragma unroll
-                        for (int kk = 0; kk < KC / 16; kk++) {
-                            const uint32_t a_off = (uint32_t)(c * (KC / 8) + kk * 2) * 128, b_off = (uint32_t)kk * 2 * 128;
-                            const uint64_t d_ahi = make_desc(smem_u32(a_hi) + a_off, 128, sbo_a);
-                            const uint64_t d_bhi = make_desc(sb + b_off, 128, (KC / 8) * 128);
-                            umma_f16(tmem, d_ahi, d_bhi, idesc, (c | kk) != 0);
-                            if (lo_b) umma_f16(tmem, d_ahi, make_desc(sb + (uint32_t)N * KC * 2 + b_off, 128, (KC / 8) * 128), idesc, 1);
-                            if (lo_a) umma_f16(tmem, make_desc(smem_u32(a_lo) + a_off, 128, sbo_a), d_bhi, idesc, 1);
-                        }
-                        umma_commit(smem_u32(empty + stage));      // frees the weight slot when these MMAs retire
-                        if (++stage == p.nstages) { stage = 0; ph ^= 1; }
-                    }
-                    umma_commit(smem_u32(acc_full));
+                for (int kk = 0; kk < KC / 16; kk++) {
+                    const uint32_t acol = (uint32_t)(kchunk * KC + kk * 16) / 2, b_off = (uint32_t)kk * 2 * 128;
+                    const uint64_t d_bhi = make_desc(sb + b_off, 128, (KC / 8) * 128);
+                    umma_ts(tmem + dcol, tmem + AH_COL + acol, d_bhi, idesc, !(fresh_acc && kk == 0));
+                    if (lo_b) umma_ts(tmem + dcol, tmem + AH_COL + acol, make_desc(sb + (uint32_t)N * KC * 2 + b_off, 128, (KC / 8) * 128), idesc, 1);
+                    if (lo_a) umma_ts(tmem + dcol, tmem + AL_COL + acol, d_bhi, idesc, 1);
                 }
+                umma_commit(smem_u32(empty + stage));              // frees the weight slot when these MMAs retire
+                if (++stage == p.nstages) { stage = 0; ph ^= 1; }
+            };
+            auto wait_a = [&](int h) { mbar_wait(smem_u32(a_ready + h), aph[h]); aph[h] ^= 1; tc_fence_after(); };
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int L = 0; L <= D; L++) {
+                    const int nk = L == 0 ? sh.nk0 : sh.nk, ks = L == 0 ? sh.k0_split : sh.k_split;
+                    const bool lo_a = L > 0 && p.precision == 0;
+                    // layer 0 overwrites z (first K chunk of each half), the residual layers accumulate onto it
+                    wait_a(0);
+                    for (int c = 0; c < ks; c++) chunk(0, Wh, c, lo_a, L == 0 && c == 0);                          // (h0, K0)
+                    if (NH == 2) {
+                        wait_a(1);
+                        for (int c = 0; c < ks; c++) chunk(Wh, Wh, c, lo_a, L == 0 && c == 0);                     // (h1, K0)
+                        for (int c = ks; c < nk; c++) chunk(0, Wh, c, lo_a, false);                               // (h0, K1)
+                    }
+                    umma_commit(smem_u32(acc_full + 0));
+                    if (NH == 2) {
+                        for (int c = ks; c < nk; c++) chunk(Wh, Wh, c, lo_a, false);                              // (h1, K1)
+                        umma_commit(smem_u32(acc_full + 1));
+                    }
+                }
+                // heads: the accumulator re-uses z's columns [0, Np): wait until both halves of z have been consumed
+                wait_a(0);
+                if (NH == 2) wait_a(1);
+                for (int c = 0; c < sh.nk; c++) chunk(0, Np, c, p.precision == 0, c == 0);
+                umma_commit(smem_u32(acc_full + 0));
             }
         }
     } else {
-        // ---- epilogue warps -------------------------------------------------------------------------------------------
+        // ---- epilogue warps -------------------------------------------------------------------------------------------------------
         const int quad = warp & 3, hh = warp >> 2;
         const int row = quad * 32 + lane;
+        const int et = threadIdx.x;                                // 0..255
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        uint32_t accph = 0;
-        int c_begin, c_end;
-        if (W >= 64) { c_begin = hh * (W / 2); c_end = c_begin + W / 2; }
-        else { c_begin = 0; c_end = hh == 0 ? W : 0; }
+        uint32_t accph[2] = {0, 0};
+        const int cph = Wh / 32;                                   // 32-column chunks per half
+        const int ch_begin = cph >= 2 ? hh * (cph / 2) : 0, ch_end = cph >= 2 ? ch_begin + cph / 2 : (hh == 0 ? cph : 0);
+        const uint8_t *brow = btile + (size_t)row * bpitch;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int m = tile * TILE_M + row;
-            const bool live = m < p.B;
-            const uint8_t *brow = p.board + (long long)(live ? m : 0) * p.board_pitch;
-            const int seat = live ? p.seats[m] : 0;
-            // observation operand (TensorIntake, heads.py:47-52): feature k = 2*cell + channel, mover's frame
-            if (hh == 0) {
-                const uint32_t sbo = (uint32_t)(K0p / 8) * 128;
-                uint8_t *dst = a_hi + (row >> 3) * sbo + (row & 7) * 16;
-                for (int j = 0; j < K0p / 8; j++) {                  // 8 features = 4 cells per 16-byte chunk
-                    uint32_t wds[4];
+            const int m0 = tile * TILE_M;
+            // ---- the tile's boards -> shared memory (coalesced 4-byte pieces), seats -------------------------------------------
+            epi_barrier();                                         // the previous tile's readers are done with btile
+            if (et < TILE_M) {
+                const int m = m0 + et;
+                int32_t sv = 0;
+                if (m < p.B) {
+                    if (p.tree_mode) {
+                        const int nd = p.tree.leaf[m];
+                        sv = nd < 0 ? -1 : ((int32_t)p.tree.node[(size_t)m * p.tree.T + nd].seat | (nd << 8));
+                    } else sv = p.seats[m];
+                } else sv = -1;
+                tseat[et] = sv;
+            }
+            epi_barrier();
+            {
+                const int wpr = (A + 3) / 4;                       // 4-byte words per board row
+                for (int i = et; i < TILE_M * wpr; i += EPI_WARPS * 32) {
+                    const int r = i / wpr, wd = i - r * wpr;
+                    const int m = m0 + r;
+                    const int32_t sv = tseat[r];
+                    uint32_t val = 0;
+                    if (m < p.B && sv >= 0) {
+                        const uint8_t *src = p.tree_mode ? p.tree.board + ((size_t)m * p.tree.T + (sv >> 8)) * p.tree.BP
+                                                         : p.board + (size_t)m * p.board_pitch;
+                        if (p.tree_mode || ((p.board_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(p.board) & 3) == 0))
+                            val = reinterpret_cast<const uint32_t *>(src)[wd];
+                        else
+                            for (int u = 0; u < 4; u++)
+                                if (wd * 4 + u < A) val |= (uint32_t)src[wd * 4 + u] << (8 * u);
+                    }
+                    *reinterpret_cast<uint32_t *>(btile + (size_t)r * bpitch + wd * 4) = val;
+                }
+            }
+            epi_barrier();
+            const int m = m0 + row;
+            const int32_t sv = tseat[row];
+            const bool live = m < p.B && sv >= 0;
+            const int seat = live ? (sv & 1) : 0;
+            // ---- observation operand (TensorIntake, heads.py:47-52): feature 2*cell + channel = one packed column per cell ---------
+            {
+                // columns split between the two warps of the quadrant when both parts are whole 16-column stores
+                const int ncol = K0p / 2;
+                const bool split = (ncol / 2) % 16 == 0;
+                const int my_cols = split ? ncol / 2 : (hh == 0 ? ncol : 0);
+                const int cb = split ? hh * (ncol / 2) : 0;
+                int r = cb / S, c = cb - r * S;                    // (row, col) of cell `cb`
+                for (int j0 = 0; j0 < my_cols; j0 += 16) {
+                    uint32_t wds[16];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int cell = j * 4 + u;
+                    for (int u = 0; u < 16; u++) {
+                        const int cell = cb + j0 + u;
                         uint32_t wd = 0;
                         if (live && cell < A) {
-                            const int r = cell / S, c = cell - r * S;
                             const uint8_t cv = brow[seat ? c * S + r : cell];
                             const bool black = cv == BL_BLACK || cv == BL_TOP || cv == BL_BOT;
                             const bool white = cv == BL_WHITE || cv == BL_LEFT || cv == BL_RIGHT;
@@ -247,73 +328,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(TcParams p) {
                             wd = (own ? 0x3C00u : 0u) | (opp ? 0x3C000000u : 0u);      // fp16 1.0
                         }
                         wds[u] = wd;
+                        if (++c == S) { c = 0; r++; }
                     }
-                    *reinterpret_cast<uint4 *>(dst + j * 128) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-                }
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(a_ready));
-
-            for (int L = 0; L <= D; L++) {
-                mbar_wait(smem_u32(acc_full), accph);
-                accph ^= 1;
-                tc_fence_after();
-                const float *bias = L == 0 ? p.b_in : p.b_res + (size_t)(L - 1) * W;
-                const float alpha = L == 0 ? 0.f : p.alpha[L - 1];
-                const bool relu_out = L < D;
-                const uint32_t sbo = (uint32_t)(W / 8) * 128;
-                uint8_t *dhi = a_hi + (row >> 3) * sbo + (row & 7) * 16, *dlo = a_lo + (row >> 3) * sbo + (row & 7) * 16;
-                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                    uint32_t acc[32], xr[32];
-                    tmem_ld32(tmem + lane_base + c0, acc);
-                    if (L > 0) tmem_ld32(tmem + lane_base + X_COL + c0, xr);
-                    tmem_wait_ld();
-                    uint32_t hi2[16], lo2[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        float y = __uint_as_float(acc[j]) + bias[c0 + j];
-                        float xn = L == 0 ? y : fmaf(alpha, y, __uint_as_float(xr[j]));
-                        xr[j] = __float_as_uint(xn);
-                        float a = relu_out ? fmaxf(xn, 0.f) : xn;
-                        __half h = __float2half_rn(a);
-                        __half l = __float2half_rn(a - __half2float(h));
-                        if (j & 1) { hi2[j >> 1] |= (uint32_t)__half_as_ushort(h) << 16; lo2[j >> 1] |= (uint32_t)__half_as_ushort(l) << 16; }
-                        else { hi2[j >> 1] = __half_as_ushort(h); lo2[j >> 1] = __half_as_ushort(l); }
-                    }
-                    tmem_st32(tmem + lane_base + X_COL + c0, xr);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        *reinterpret_cast<uint4 *>(dhi + (c0 / 8 + u) * 128) = make_uint4(hi2[4 * u], hi2[4 * u + 1], hi2[4 * u + 2], hi2[4 * u + 3]);
-                        *reinterpret_cast<uint4 *>(dlo + (c0 / 8 + u) * 128) = make_uint4(lo2[4 * u], lo2[4 * u + 1], lo2[4 * u + 2], lo2[4 * u + 3]);
-                    }
+                    tmem_st16(tmem + lane_base + AH_COL + cb + j0, wds);
                 }
                 tmem_wait_st();
-                fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(a_ready));
+                if (lane == 0) { mbar_arrive(smem_u32(a_ready + 0)); if (NH == 2) mbar_arrive(smem_u32(a_ready + 1)); }
             }
-            // ---- heads --------------------------------------------------------------------------------------------------
-            mbar_wait(smem_u32(acc_full), accph);
-            accph ^= 1;
+            // ---- body layers: z -> next operand -------------------------------------------------------------------------------------
+            for (int L = 0; L <= D; L++) {
+                const float *cb = p.cbias + (size_t)L * W;
+                const bool relu_out = L < D;
+                for (int h = 0; h < NH; h++) {
+                    // layer 0's one-hot operand lives in the very columns the next operand is written to, under a different
+                    // K <-> column mapping: nothing may be overwritten before ALL of layer 0's MMAs have retired
+                    if (L == 0 && NH == 2) {
+                        if (h == 0) { mbar_wait(smem_u32(acc_full + 0), accph[0]); mbar_wait(smem_u32(acc_full + 1), accph[1]); accph[0] ^= 1; accph[1] ^= 1; }
+                    } else {
+                        mbar_wait(smem_u32(acc_full + h), accph[h]);
+                        accph[h] ^= 1;
+                    }
+                    tc_fence_after();
+                    for (int ch = ch_begin; ch < ch_end; ch++) {
+                        const int col = h * Wh + ch * 32;
+                        uint32_t acc[32];
+                        tmem_ld32(tmem + lane_base + col, acc);
+                        tmem_wait_ld();
+                        uint32_t hi2[16], lo2[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 c4 = *reinterpret_cast<const float4 *>(cb + col + j);
+                            float a0 = __uint_as_float(acc[j]) + c4.x, a1 = __uint_as_float(acc[j + 1]) + c4.y;
+                            float a2 = __uint_as_float(acc[j + 2]) + c4.z, a3 = __uint_as_float(acc[j + 3]) + c4.w;
+                            if (relu_out) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                            const uint32_t h01 = pack_h2(a0, a1), h23 = pack_h2(a2, a3);
+                            const float2 f01 = __half22float2(*reinterpret_cast<const __half2 *>(&h01));
+                            const float2 f23 = __half22float2(*reinterpret_cast<const __half2 *>(&h23));
+                            hi2[j / 2] = h01; hi2[j / 2 + 1] = h23;
+                            lo2[j / 2] = pack_h2(a0 - f01.x, a1 - f01.y); lo2[j / 2 + 1] = pack_h2(a2 - f23.x, a3 - f23.y);
+                        }
+                        tmem_st16(tmem + lane_base + AH_COL + col / 2, hi2);
+                        if (p.precision == 0) tmem_st16(tmem + lane_base + AL_COL + col / 2, lo2);
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(a_ready + h));
+                }
+            }
+            // ---- heads -----------------------------------------------------------------------------------------------------------------
+            mbar_wait(smem_u32(acc_full + 0), accph[0]);
+            accph[0] ^= 1;
             tc_fence_after();
             if (hh == 0) {
+                const float *bh = p.cbias + (size_t)(D + 1) * W;
                 float mx = -BL_INF_F, tanh_v = 0.f;
                 for (int c0 = 0; c0 < Np; c0 += 32) {
                     uint32_t acc[32];
                     tmem_ld32(tmem + lane_base + c0, acc);
                     tmem_wait_ld();
+                    int r = c0 / S, c = c0 - r * S;
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const int a = c0 + j;
                         if (a < A) {
-                            const int r = a / S, c = a - r * S;
-                            if (brow[seat ? c * S + r : a] == BL_EMPTY) mx = fmaxf(mx, __uint_as_float(acc[j]) + p.b_head[a]);
+                            if (brow[seat ? c * S + r : a] == BL_EMPTY) mx = fmaxf(mx, __uint_as_float(acc[j]) + bh[a]);
                         } else if (a == A) {
-                            tanh_v = tanhf(__uint_as_float(acc[j]) + p.b_head[A]);
+                            tanh_v = tanhf(__uint_as_float(acc[j]) + bh[A]);
                         }
+                        if (++c == S) { c = 0; r++; }
                     }
                 }
                 float sum = 0.f;
@@ -321,35 +406,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(TcParams p) {
                     uint32_t acc[32];
                     tmem_ld32(tmem + lane_base + c0, acc);
                     tmem_wait_ld();
+                    int r = c0 / S, c = c0 - r * S;
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const int a = c0 + j;
-                        if (a < A) {
-                            const int r = a / S, c = a - r * S;
-                            if (brow[seat ? c * S + r : a] == BL_EMPTY) sum += expf((__uint_as_float(acc[j]) + p.b_head[a]) - mx);
-                        }
+                        if (a < A && brow[seat ? c * S + r : a] == BL_EMPTY) sum += expf((__uint_as_float(acc[j]) + bh[a]) - mx);
+                        if (++c == S) { c = 0; r++; }
                     }
                 }
                 const float lse = logf(sum);
+                // tree mode: logits -> half -> exp table -> pi row + row summary, straight into the search tree (what
+                // bl_tree_set_eval does for injected evaluations); otherwise fp32 logits / v for the caller
+                const int nd = sv >> 8;
+                const size_t slot = p.tree_mode && live ? (size_t)m * p.tree.T + nd : 0;
+                float pmax = 0.f, pmin = BL_INF_F;
+                int fz = 255, lz = -1;
                 for (int c0 = 0; c0 < Np; c0 += 32) {
                     uint32_t acc[32];
                     tmem_ld32(tmem + lane_base + c0, acc);
                     tmem_wait_ld();
                     if (live) {
+                        int r = c0 / S, c = c0 - r * S;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const int a = c0 + j;
-                            if (a < A) {
-                                const int r = a / S, c = a - r * S;
-                                const bool valid = brow[seat ? c * S + r : a] == BL_EMPTY;
-                                p.logits[(size_t)m * A + a] = valid ? ((__uint_as_float(acc[j]) + p.b_head[a]) - mx) - lse : -BL_INF_F;
+                        for (int j0 = 0; j0 < 32; j0 += 4) {
+                            float out[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int a = c0 + j0 + u;
+                                float lg = -BL_INF_F;
+                                if (a < A && brow[seat ? c * S + r : a] == BL_EMPTY) lg = ((__uint_as_float(acc[j0 + u]) + bh[a]) - mx) - lse;
+                                if (p.tree_mode) {
+                                    const bl_half hl = bl_f2h(lg);
+                                    float pv = a < A ? p.tree.exp_lut[hl] : 0.f;
+                                    if (a < A && p.tree.logits) p.tree.logits[slot * A + a] = hl;
+                                    if (pv != 0.f) { pmax = fmaxf(pmax, pv); pmin = fminf(pmin, pv); fz = min(fz, a); lz = max(lz, a); }
+                                    out[u] = pv;
+                                } else if (a < A) p.logits[(size_t)m * A + a] = lg;
+                                if (++c == S) { c = 0; r++; }
                             }
+                            if (p.tree_mode && c0 + j0 < p.tree.AP)
+                                *reinterpret_cast<float4 *>(p.tree.pi + slot * p.tree.AP + c0 + j0) = make_float4(out[0], out[1], out[2], out[3]);
                         }
                     }
                 }
                 if (live) {
-                    p.v[(size_t)m * 2 + seat] = tanh_v;
-                    p.v[(size_t)m * 2 + (1 - seat)] = -tanh_v;
+                    const float v0 = seat ? -tanh_v : tanh_v, v1 = -v0;
+                    if (p.tree_mode) {
+                        uint32_t *ax = reinterpret_cast<uint32_t *>(p.tree.aux + slot);
+                        ax[1] = (uint32_t)bl_f2h(v0) | ((uint32_t)bl_f2h(v1) << 16);
+                        reinterpret_cast<uint2 *>(ax)[1] = make_uint2(__float_as_uint(pmax), (__float_as_uint(pmin) >> 16) | ((uint32_t)(fz & 255) << 16) |
+                                                                                                   ((uint32_t)((lz < 0 ? 0 : lz) & 255) << 24));
+                    } else {
+                        p.v[(size_t)m * 2] = v0;
+                        p.v[(size_t)m * 2 + 1] = v1;
+                    }
                 }
             }
             tc_fence_before();
@@ -360,26 +470,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(TcParams p) {
     if (warp == WARP_MMA) tmem_dealloc(tmem, 512);
 }
 
-}  // namespace
-
-// Host-side launcher, called from bl_fc_forward (net.cu) when a packed operand blob is present and the shape fits.
-int bl_fc_forward_tc(const bl_fc_params *p, const uint8_t *board, long long board_pitch, const int32_t *seats, float *logits,
-                     float *v, int B, cudaStream_t st) {
+int launch(const bl_fc_params *p, TcParams &k, int B, cudaStream_t st) {
     const int S = p->S, A = S * S, W = p->W;
-    TcParams k;
-    k.board = board; k.seats = seats; k.board_pitch = board_pitch;
     k.blob = reinterpret_cast<const uint8_t *>(p->packed);
-    k.b_in = p->b_in; k.b_res = p->b_res; k.alpha = p->alpha; k.b_head = p->b_head;
-    k.logits = logits; k.v = v;
+    k.cbias = p->b_head;
     k.B = B; k.S = S; k.A = A; k.W = W; k.D = p->D; k.precision = p->precision;
     k.K0p = (2 * A + KC - 1) / KC * KC;
     k.Np = (A + 1 + 31) / 32 * 32;
-    size_t a, b, c;
+    const Shape sh = make_shape(W, k.K0p, k.Np);
     int ns = MAX_STAGES;
-    while (ns >= 2 && carve_sizes(W, k.K0p, k.Np, ns, &a, &b, &c) > 227 * 1024) ns--;
+    while (ns >= 2 && smem_bytes(sh, ns, A) > 227 * 1024) ns--;
     if (ns < 2) return -2;
     k.nstages = ns;
-    const size_t smem = carve_sizes(W, k.K0p, k.Np, ns, &a, &b, &c);
+    const size_t smem = smem_bytes(sh, ns, A);
     cudaError_t e = cudaFuncSetAttribute(fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int ntiles = (B + TILE_M - 1) / TILE_M;
@@ -388,8 +491,29 @@ int bl_fc_forward_tc(const bl_fc_params *p, const uint8_t *board, long long boar
     return (int)cudaGetLastError();
 }
 
-// shapes the tensor-core path covers: W in {32, 64, 128, 256} (tile N = W <= 256 TMEM columns next to the residual stream)
+}  // namespace
+
+// Host-side launcher, called from bl_fc_forward (net.cu) when a packed operand blob is present and the shape fits.
+int bl_fc_forward_tc(const bl_fc_params *p, const uint8_t *board, long long board_pitch, const int32_t *seats, float *logits,
+                     float *v, int B, cudaStream_t st) {
+    TcParams k = {};
+    k.board = board; k.seats = seats; k.board_pitch = board_pitch;
+    k.logits = logits; k.v = v;
+    k.tree_mode = 0;
+    return launch(p, k, B, st);
+}
+
+// Leaf evaluation straight from / into the search tree (bl_tree_eval_leaves): no gather, no fp32 logits round trip, no set_eval.
+int bl_fc_forward_tc_tree(const bl_fc_params *p, const bl_tree *t, cudaStream_t st) {
+    TcParams k = {};
+    k.tree_mode = 1;
+    k.tree = *t;
+    return launch(p, k, t->B, st);
+}
+
+// shapes the tensor-core path covers: W in {32, 64, 128, 256} (z fits 256 TMEM columns, the operand regions 2 x 128), S <= 13
 bool bl_fc_tc_supported(const bl_fc_params *p) {
     const int A = p->S * p->S, W = p->W;
-    return p->packed != nullptr && p->b_head != nullptr && (W == 32 || W == 64 || W == 128 || W == 256) && A + 1 <= 256;
+    const int K0p = (2 * A + KC - 1) / KC * KC;
+    return p->packed != nullptr && p->b_head != nullptr && (W == 32 || W == 64 || W == 128 || W == 256) && A + 1 <= 256 && K0p / 2 <= 256;
 }

@@ -103,7 +103,7 @@ class SearchEngine:
     def eval_root(self, cparams):
         check(_lib.lib().bl_tree_eval_root(self._tp, ctypes.byref(cparams), ptr(self.root_logits), ptr(self.root_v),
                                            ptr(self.scratch_for(cparams)), self._stream()), 'bl_tree_eval_root')
-        self.launches += cparams.D + 4         # gather + intake + D residuals + policy + heads
+        self.launches += 2 if _lib.lib().bl_fc_uses_tensor_cores(ctypes.byref(cparams)) else cparams.D + 4
         return self.root_logits, self.root_v
 
     def set_eval(self, node, logits, v):
@@ -126,7 +126,8 @@ class SearchEngine:
     def eval_leaves(self, cparams, sim):
         check(_lib.lib().bl_tree_eval_leaves(self._tp, ctypes.byref(cparams), sim, ptr(self.scratch_for(cparams)),
                                              self._stream()), 'bl_tree_eval_leaves')
-        self.launches += cparams.D + 5         # gather + network (D+3) + set_eval
+        # tensor-core path: one fused kernel; CUDA-core path: gather + network (D+3) + set_eval
+        self.launches += 1 if _lib.lib().bl_fc_uses_tensor_cores(ctypes.byref(cparams)) else cparams.D + 5
 
     def backup(self, sim):
         check(_lib.lib().bl_tree_backup(self._tp, sim, self._stream()), 'bl_tree_backup')

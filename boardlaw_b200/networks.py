@@ -134,21 +134,38 @@ def _split_tiles(w, n_pad, k_pad):
 
 
 def pack_tensor_core_operands(pack, boardsize):
-    """The weight blob fc_tc_kernel streams: layer 0 tiles, the residual layers' tiles, then the fused head
-    [policy ; value] — each weight split as hi = fp16(w), lo = fp16(w - hi)."""
+    """The weight blob fc_tc_kernel streams, in the kernel's consumption order (net_tc.cu): per layer the four blocks
+    (N half 0, K half 0), (N half 1, K half 0), (N half 0, K half 1), (N half 1, K half 1) — one block when W < 64 — then the
+    fused head [policy ; value]; every weight split as hi = fp16(w), lo = fp16(w - hi).  The ReZero gate is folded into the
+    residual weights (alpha_k W_k), and the biases are returned as the cumulative vectors c_0 = b_in, c_k = c_{k-1} +
+    alpha_k b_k the kernel adds on the way out of the accumulator, followed by the head bias."""
     A = boardsize * boardsize
     W = pack['w_in'].shape[0]
     k0p = (2 * A + KC - 1) // KC * KC
     n_p = (A + 1 + 31) // 32 * 32
-    parts = [_split_tiles(pack['w_in'], W, k0p).reshape(-1)]
+    nh = 2 if W >= 64 else 1
+    wh = W // nh
+
+    def body(w, k_pad):
+        nk = k_pad // KC
+        ks = ((nk + 1) // 2 if k_pad == k0p and w is pack['w_in'] else nk // 2) if nh == 2 else nk
+        tiles = [_split_tiles(w[h * wh:(h + 1) * wh], wh, k_pad) for h in range(nh)]      # (nk, 2, wh/8, KC/8, 8, 8) each
+        if nh == 1:
+            return [tiles[0].reshape(-1)]
+        return [tiles[0][:ks].reshape(-1), tiles[1][:ks].reshape(-1), tiles[0][ks:].reshape(-1), tiles[1][ks:].reshape(-1)]
+
+    parts = body(pack['w_in'], k0p)
+    cb = [pack['b_in']]
     for k in range(pack['w_res'].shape[0]):
-        parts.append(_split_tiles(pack['w_res'][k], W, W).reshape(-1))
+        alpha = pack['alpha'][k]
+        parts += body(alpha * pack['w_res'][k], W)
+        cb.append(cb[-1] + alpha * pack['b_res'][k])
     head = torch.cat([pack['w_pol'], pack['w_val'][None]], 0)            # (A+1, W)
     parts.append(_split_tiles(head, n_p, W).reshape(-1))
     b_head = pack['b_pol'].new_zeros((n_p,))
     b_head[:A] = pack['b_pol']
     b_head[A] = pack['b_val'][0]
-    return torch.cat(parts).contiguous(), b_head
+    return torch.cat(parts).contiguous(), torch.cat([torch.stack(cb).reshape(-1), b_head]).contiguous()
 
 
 def synthetic_state_dict(boardsize, width, depth, seed=0):

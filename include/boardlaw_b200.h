@@ -126,10 +126,16 @@ typedef struct bl_fc_params {
     const float *b_pol;   /* (A,)     policy.core.bias    */
     const float *w_val;   /* (W,)     value.core.weight   */
     const float *b_val;   /* (1,)     value.core.bias     */
-    const void *packed;   /* tensor-core operand tiles (split-fp16, UMMA canonical K-major layout) built by the
-                             host packer, boardlaw_b200/networks.py:pack_tensor_core_operands; NULL: CUDA-core path */
-    const float *b_head;  /* (roundup(A+1,32),) = [policy bias (A), value bias, zeros]; with `packed`             */
+    const void *packed;   /* tensor-core operand tiles (split-fp16, UMMA canonical K-major layout, ReZero gate folded in)
+                             in the kernel's consumption order, built by the host packer
+                             boardlaw_b200/networks.py:pack_tensor_core_operands; NULL: CUDA-core path              */
+    const float *b_head;  /* with `packed`: (D+1, W) cumulative biases c_0 = b_in, c_k = c_{k-1} + alpha_k b_k, then
+                             (roundup(A+1,32),) = [policy bias (A), value bias, zeros]                              */
 } bl_fc_params;
+
+/* 1 when bl_fc_forward / bl_tree_eval_leaves run this shape on the tcgen05 kernel (W in {32,64,128,256}, packed operands
+ * present), 0 when they run the CUDA-core kernels. */
+int bl_fc_uses_tensor_cores(const bl_fc_params *p);
 
 /* Bytes of device scratch bl_fc_forward needs for a batch of B envs. */
 int64_t bl_fc_scratch_bytes(const bl_fc_params *p, int B);
