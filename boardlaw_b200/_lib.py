@@ -13,7 +13,7 @@ import torch
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / 'libboardlaw_b200.so'
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class FCParams(Structure):
@@ -21,7 +21,7 @@ class FCParams(Structure):
     _fields_ = [('S', c_int), ('W', c_int), ('D', c_int), ('precision', c_int),
                 ('w_in', c_void_p), ('b_in', c_void_p), ('w_res', c_void_p), ('b_res', c_void_p),
                 ('alpha', c_void_p), ('w_pol', c_void_p), ('b_pol', c_void_p), ('w_val', c_void_p),
-                ('b_val', c_void_p), ('packed', c_void_p), ('b_head', c_void_p)]
+                ('b_val', c_void_p), ('packed', c_void_p), ('b_head', c_void_p), ('tc_nsplit', c_int)]
 
 
 class Tree(Structure):

@@ -566,6 +566,8 @@ int bl_descend_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed
     return bl_expand_step(t, sim, st);
 }
 
+unsigned long long *bl_phase_prof() { return g_phase_prof; }
+
 extern "C" int bl_debug_set_phase_profile(uint64_t *buf) {
     g_phase_prof = reinterpret_cast<unsigned long long *>(buf);
     return 0;

@@ -59,3 +59,5 @@ __device__ __forceinline__ float bl_minnz(const bl_aux &a) { return __uint_as_fl
 int bl_descend_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
 // descend.cu: expand + env step of the descents recorded in t.leaf / leaf_parent / leaf_action
 int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st);
+// descend.cu: device buffer of the optional phase clock (NULL = off); slots 0..15 descent, 16..31 network
+unsigned long long *bl_phase_prof();

@@ -45,9 +45,10 @@ struct TcParams {
     const uint8_t *blob;                   // packed operand tiles, in consumption order
     const float *cbias;                    // (D+1, W) cumulative biases c_k, then (Np) head bias
     float *logits, *v;                     // (B,A), (B,2) fp32 outputs (NULL in tree mode)
-    int B, S, A, W, D, K0p, Np, precision, nstages;
+    int B, S, A, W, D, K0p, Np, precision, nstages, nsplit;
     int tree_mode;                         // 1: inputs are the current leaves of `tree`, outputs go straight into the tree
     bl_tree tree;
+    unsigned long long *prof;              // optional phase clock (bl_debug_set_phase_profile), slots 16..31
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -142,9 +143,9 @@ struct Shape {              // derived sizes shared by the three roles and the h
     int k0_split, k_split;  // chunks in the first K half (layer 0 / other layers)
     uint32_t stage_bytes;
 };
-__host__ __device__ inline Shape make_shape(int W, int K0p, int Np) {
+__host__ __device__ inline Shape make_shape(int W, int K0p, int Np, int nsplit) {
     Shape s;
-    s.NH = W >= 64 ? 2 : 1;
+    s.NH = (nsplit == 2 && W >= 64) ? 2 : 1;
     s.Wh = W / s.NH;
     s.nk0 = K0p / KC;
     s.nk = W / KC;
@@ -156,19 +157,24 @@ __host__ __device__ inline Shape make_shape(int W, int K0p, int Np) {
 }
 __host__ __device__ inline int board_pitch_bytes(int A) { return 4 * (((A + 3) / 4) | 1); }   // odd number of words: conflict-free rows
 size_t smem_bytes(const Shape &s, int nstages, int A) {
-    return (size_t)s.stage_bytes * nstages + (size_t)TILE_M * board_pitch_bytes(A) + 1024;
+    return (size_t)s.stage_bytes * nstages + (size_t)TILE_M * board_pitch_bytes(A) + 1024 + 12 * TILE_M * sizeof(float);
 }
+size_t bias_bytes(int W, int D, int Np) { return ((size_t)(D + 1) * W + Np) * sizeof(float); }
+
+#define TCK(k) do { if (p.prof) { const long long now_ = clock64(); pc[k] += now_ - tl; tl = now_; } } while (0)
 
 __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const Shape sh = make_shape(p.W, p.K0p, p.Np);
+    const Shape sh = make_shape(p.W, p.K0p, p.Np, p.nsplit);
     const int bpitch = board_pitch_bytes(p.A);                     // board tile row pitch
     uint8_t *stage0 = smem;
     uint8_t *btile = stage0 + (size_t)sh.stage_bytes * p.nstages;  // [TILE_M][bpitch] boards of the tile
     uint64_t *bars = reinterpret_cast<uint64_t *>(btile + (size_t)TILE_M * bpitch + ((16 - ((size_t)TILE_M * bpitch) % 16) % 16));
     uint64_t *full = bars, *empty = bars + MAX_STAGES, *a_ready = bars + 2 * MAX_STAGES, *acc_full = a_ready + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 2);
-    int32_t *tseat = reinterpret_cast<int32_t *>(tmem_ptr + 2);   // [TILE_M] seat | node << 8 of the tile's rows
+    int32_t *tseat = reinterpret_cast<int32_t *>(tmem_ptr + 4);   // [TILE_M] seat | node << 8 of the tile's rows
+    float *xch = reinterpret_cast<float *>(tseat + TILE_M);       // [12][TILE_M] partial results exchanged between the two warps of a quadrant
+    float *sbias = xch + 12 * TILE_M;                             // (D+1, W) cumulative biases, then the head bias (Np)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.W, D = p.D, A = p.A, S = p.S, Np = p.Np, K0p = p.K0p;
@@ -181,6 +187,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_ptr), 512);
+    for (int i = threadIdx.x; i < (p.D + 1) * p.W + p.Np; i += TC_THREADS) sbias[i] = p.cbias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -213,9 +220,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
             int stage = 0;
             uint32_t ph = 0, aph[2] = {0, 0};
             const bool lo_b = p.precision == 0;
+            long long pc[3] = {0, 0, 0}, tl = p.prof ? clock64() : 0;       // [0] wait operand, [1] wait weights, [2] issue
             // one K chunk (KC = 2 K-steps of 16) of one N block: D columns [dcol, dcol+N), A columns from acol
             auto chunk = [&](uint32_t dcol, int N, int kchunk, bool lo_a, bool fresh_acc) {
+                TCK(2);
                 mbar_wait(smem_u32(full + stage), ph);
+                TCK(1);
                 tc_fence_after();
                 const uint32_t sb = smem_u32(stage0 + (size_t)sh.stage_bytes * stage);
                 const uint32_t idesc = make_idesc(TILE_M, N);
@@ -230,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                 umma_commit(smem_u32(empty + stage));              // frees the weight slot when these MMAs retire
                 if (++stage == p.nstages) { stage = 0; ph ^= 1; }
             };
-            auto wait_a = [&](int h) { mbar_wait(smem_u32(a_ready + h), aph[h]); aph[h] ^= 1; tc_fence_after(); };
+            auto wait_a = [&](int h) { TCK(2); mbar_wait(smem_u32(a_ready + h), aph[h]); TCK(0); aph[h] ^= 1; tc_fence_after(); };
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int L = 0; L <= D; L++) {
                     const int nk = L == 0 ? sh.nk0 : sh.nk, ks = L == 0 ? sh.k0_split : sh.k_split;
@@ -255,6 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                 for (int c = 0; c < sh.nk; c++) chunk(0, Np, c, p.precision == 0, c == 0);
                 umma_commit(smem_u32(acc_full + 0));
             }
+            if (p.prof) { TCK(2); for (int k = 0; k < 3; k++) atomicAdd(p.prof + 16 + k, (unsigned long long)pc[k]); atomicAdd(p.prof + 31, 1ull); }
         }
     } else {
         // ---- epilogue warps -------------------------------------------------------------------------------------------------------
@@ -263,45 +274,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
         const int et = threadIdx.x;                                // 0..255
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         uint32_t accph[2] = {0, 0};
+        long long pc[6] = {0, 0, 0, 0, 0, 0}, tl = p.prof ? clock64() : 0;   // [0] board staging [1] obs [2] wait acc [3] body epilogue [4] heads [5] wait heads
         const int cph = Wh / 32;                                   // 32-column chunks per half
         const int ch_begin = cph >= 2 ? hh * (cph / 2) : 0, ch_end = cph >= 2 ? ch_begin + cph / 2 : (hh == 0 ? cph : 0);
         const uint8_t *brow = btile + (size_t)row * bpitch;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int m0 = tile * TILE_M;
-            // ---- the tile's boards -> shared memory (coalesced 4-byte pieces), seats -------------------------------------------
-            epi_barrier();                                         // the previous tile's readers are done with btile
-            if (et < TILE_M) {
-                const int m = m0 + et;
-                int32_t sv = 0;
-                if (m < p.B) {
-                    if (p.tree_mode) {
-                        const int nd = p.tree.leaf[m];
-                        sv = nd < 0 ? -1 : ((int32_t)p.tree.node[(size_t)m * p.tree.T + nd].seat | (nd << 8));
-                    } else sv = p.seats[m];
-                } else sv = -1;
-                tseat[et] = sv;
-            }
-            epi_barrier();
-            {
-                const int wpr = (A + 3) / 4;                       // 4-byte words per board row
-                for (int i = et; i < TILE_M * wpr; i += EPI_WARPS * 32) {
-                    const int r = i / wpr, wd = i - r * wpr;
-                    const int m = m0 + r;
-                    const int32_t sv = tseat[r];
-                    uint32_t val = 0;
-                    if (m < p.B && sv >= 0) {
-                        const uint8_t *src = p.tree_mode ? p.tree.board + ((size_t)m * p.tree.T + (sv >> 8)) * p.tree.BP
-                                                         : p.board + (size_t)m * p.board_pitch;
-                        if (p.tree_mode || ((p.board_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(p.board) & 3) == 0))
-                            val = reinterpret_cast<const uint32_t *>(src)[wd];
-                        else
-                            for (int u = 0; u < 4; u++)
-                                if (wd * 4 + u < A) val |= (uint32_t)src[wd * 4 + u] << (8 * u);
+        const float *bh = sbias + (size_t)(D + 1) * W;             // head bias
+        // board staging: two threads per row, each moves half of the row's 4-byte words; the NEXT tile's words travel in
+        // registers while the current tile is computed
+        constexpr int MAXW = 22;                                   // words per thread: A <= 169 -> 43 words per row
+        const int wpr = (A + 3) / 4, wfirst = (et & 1) ? (wpr + 1) / 2 : 0, wcount = (et & 1) ? wpr / 2 : (wpr + 1) / 2;
+        const int srow = et >> 1;
+        uint32_t bw[MAXW];
+        int32_t sv_next = -1;
+        auto fetch_tile = [&](int tile) {                          // issue the loads of `tile`'s board words and seat for row `srow`
+            const int m = tile * TILE_M + srow;
+            sv_next = -1;
+#pragma unroll
+            for (int k = 0; k < MAXW; k++) bw[k] = 0;
+            if (tile < ntiles && m < p.B) {
+                const uint8_t *src;
+                if (p.tree_mode) {
+                    const int nd = p.tree.leaf[m];
+                    if (nd >= 0) {
+                        sv_next = (int32_t)p.tree.node[(size_t)m * p.tree.T + nd].seat | (nd << 8);
+                        src = p.tree.board + ((size_t)m * p.tree.T + nd) * p.tree.BP;
                     }
-                    *reinterpret_cast<uint32_t *>(btile + (size_t)r * bpitch + wd * 4) = val;
+                } else {
+                    sv_next = p.seats[m];
+                    src = p.board + (size_t)m * p.board_pitch;
+                }
+                if (sv_next >= 0) {
+                    if (p.tree_mode || ((p.board_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(p.board) & 3) == 0)) {
+#pragma unroll
+                        for (int k = 0; k < MAXW; k++)
+                            if (k < wcount) bw[k] = reinterpret_cast<const uint32_t *>(src)[wfirst + k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < MAXW; k++)
+                            if (k < wcount)
+                                for (int u = 0; u < 4; u++)
+                                    if ((wfirst + k) * 4 + u < A) bw[k] |= (uint32_t)src[(wfirst + k) * 4 + u] << (8 * u);
+                    }
                 }
             }
+        };
+        fetch_tile(blockIdx.x);
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m0 = tile * TILE_M;
+            // ---- the tile's boards (fetched during the previous tile) -> shared memory --------------------------------------------
+            epi_barrier();                                         // the previous tile's readers are done with btile
+#pragma unroll
+            for (int k = 0; k < MAXW; k++)
+                if (k < wcount) *reinterpret_cast<uint32_t *>(btile + (size_t)srow * bpitch + (wfirst + k) * 4) = bw[k];
+            if ((et & 1) == 0) tseat[srow] = sv_next;
             epi_barrier();
+            fetch_tile(tile + gridDim.x);
+            TCK(0);
             const int m = m0 + row;
             const int32_t sv = tseat[row];
             const bool live = m < p.B && sv >= 0;
@@ -313,6 +341,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                 const bool split = (ncol / 2) % 16 == 0;
                 const int my_cols = split ? ncol / 2 : (hh == 0 ? ncol : 0);
                 const int cb = split ? hh * (ncol / 2) : 0;
+                // cell codes: black = {1,3,4}, white = {2,5,6} (hex_core.cuh); channel 0 = the mover's own stones
+                const uint32_t own_mask = seat ? 0x64u : 0x1Au, opp_mask = seat ? 0x1Au : 0x64u;
                 int r = cb / S, c = cb - r * S;                    // (row, col) of cell `cb`
                 for (int j0 = 0; j0 < my_cols; j0 += 16) {
                     uint32_t wds[16];
@@ -321,11 +351,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                         const int cell = cb + j0 + u;
                         uint32_t wd = 0;
                         if (live && cell < A) {
-                            const uint8_t cv = brow[seat ? c * S + r : cell];
-                            const bool black = cv == BL_BLACK || cv == BL_TOP || cv == BL_BOT;
-                            const bool white = cv == BL_WHITE || cv == BL_LEFT || cv == BL_RIGHT;
-                            const bool own = seat ? white : black, opp = seat ? black : white;
-                            wd = (own ? 0x3C00u : 0u) | (opp ? 0x3C000000u : 0u);      // fp16 1.0
+                            const uint32_t cv = brow[seat ? c * S + r : cell];
+                            wd = ((own_mask >> cv) & 1u) * 0x3C00u | ((opp_mask >> cv) & 1u) * 0x3C000000u;      // fp16 1.0
                         }
                         wds[u] = wd;
                         if (++c == S) { c = 0; r++; }
@@ -337,9 +364,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(smem_u32(a_ready + 0)); if (NH == 2) mbar_arrive(smem_u32(a_ready + 1)); }
             }
+            TCK(1);
             // ---- body layers: z -> next operand -------------------------------------------------------------------------------------
             for (int L = 0; L <= D; L++) {
-                const float *cb = p.cbias + (size_t)L * W;
+                const float *cb = sbias + (size_t)L * W;
                 const bool relu_out = L < D;
                 for (int h = 0; h < NH; h++) {
                     // layer 0's one-hot operand lives in the very columns the next operand is written to, under a different
@@ -351,11 +379,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                         accph[h] ^= 1;
                     }
                     tc_fence_after();
+                    TCK(2);
+                    uint32_t nxt[32];
+                    if (ch_begin < ch_end) tmem_ld32(tmem + lane_base + h * Wh + ch_begin * 32, nxt);
                     for (int ch = ch_begin; ch < ch_end; ch++) {
                         const int col = h * Wh + ch * 32;
                         uint32_t acc[32];
-                        tmem_ld32(tmem + lane_base + col, acc);
                         tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) acc[j] = nxt[j];
+                        if (ch + 1 < ch_end) tmem_ld32(tmem + lane_base + col + 32, nxt);      // in flight during this chunk's arithmetic
                         uint32_t hi2[16], lo2[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -376,94 +409,137 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(a_ready + h));
+                    TCK(3);
                 }
             }
-            // ---- heads -----------------------------------------------------------------------------------------------------------------
+            // ---- heads: masked log-softmax + tanh; the two warps of a quadrant share a row's columns in 16-column units ---------
             mbar_wait(smem_u32(acc_full + 0), accph[0]);
             accph[0] ^= 1;
             tc_fence_after();
-            if (hh == 0) {
-                const float *bh = p.cbias + (size_t)(D + 1) * W;
+            TCK(5);
+            {
+                const int nu = Np / 16, u_begin = hh ? nu / 2 : 0, u_end = hh ? nu : nu / 2;
+                // which of my columns are legal moves (cell empty), as a bitmask: bit (u - u_begin)*16 + j; at most 6 units per warp
+                unsigned long long vm0 = 0, vm1 = 0;
+                {
+                    int r = (u_begin * 16) / S, c = u_begin * 16 - r * S;
+                    const int ncols = (u_end - u_begin) * 16;
+                    for (int j = 0; j < ncols; j++) {
+                        const int a = u_begin * 16 + j;
+                        const unsigned long long bit = (a < A && brow[seat ? c * S + r : a] == BL_EMPTY) ? 1ull : 0ull;
+                        if (j < 64) vm0 |= bit << j; else vm1 |= bit << (j - 64);
+                        if (++c == S) { c = 0; r++; }
+                    }
+                }
+                auto ld16 = [&](int u, uint32_t (&acc)[16]) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
+                                   "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]), "=r"(acc[15])
+                                 : "r"(tmem + lane_base + u * 16) : "memory");
+                    tmem_wait_ld();
+                };
+                auto bits16 = [&](int u) { const int sft = (u - u_begin) * 16; return (uint32_t)((sft < 64 ? vm0 >> sft : vm1 >> (sft - 64)) & 0xFFFFull); };
+                // pass 1: raw logits of the valid actions -> max; the value head's column sits right after the policy's
                 float mx = -BL_INF_F, tanh_v = 0.f;
-                for (int c0 = 0; c0 < Np; c0 += 32) {
-                    uint32_t acc[32];
-                    tmem_ld32(tmem + lane_base + c0, acc);
-                    tmem_wait_ld();
-                    int r = c0 / S, c = c0 - r * S;
+                for (int u = u_begin; u < u_end; u++) {
+                    uint32_t acc[16];
+                    ld16(u, acc);
+                    const uint32_t vb = bits16(u);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int a = c0 + j;
-                        if (a < A) {
-                            if (brow[seat ? c * S + r : a] == BL_EMPTY) mx = fmaxf(mx, __uint_as_float(acc[j]) + bh[a]);
-                        } else if (a == A) {
-                            tanh_v = tanhf(__uint_as_float(acc[j]) + bh[A]);
-                        }
-                        if (++c == S) { c = 0; r++; }
+                    for (int j = 0; j < 16; j++) {
+                        const float x = __uint_as_float(acc[j]) + bh[u * 16 + j];
+                        if ((vb >> j) & 1u) mx = fmaxf(mx, x);
+                        if (u * 16 + j == A) tanh_v = tanhf(x);
                     }
                 }
+                xch[hh * TILE_M + row] = mx;
+                xch[(2 + hh) * TILE_M + row] = tanh_v;
+                epi_barrier();
+                mx = fmaxf(mx, xch[(hh ^ 1) * TILE_M + row]);
+                tanh_v += xch[(2 + (hh ^ 1)) * TILE_M + row];          // exactly one of the two warps saw column A
+                // pass 2: sum of exp
                 float sum = 0.f;
-                for (int c0 = 0; c0 < Np; c0 += 32) {
-                    uint32_t acc[32];
-                    tmem_ld32(tmem + lane_base + c0, acc);
-                    tmem_wait_ld();
-                    int r = c0 / S, c = c0 - r * S;
+                for (int u = u_begin; u < u_end; u++) {
+                    uint32_t acc[16];
+                    ld16(u, acc);
+                    const uint32_t vb = bits16(u);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int a = c0 + j;
-                        if (a < A && brow[seat ? c * S + r : a] == BL_EMPTY) sum += expf((__uint_as_float(acc[j]) + bh[a]) - mx);
-                        if (++c == S) { c = 0; r++; }
-                    }
+                    for (int j = 0; j < 16; j++)
+                        if ((vb >> j) & 1u) sum += __expf((__uint_as_float(acc[j]) + bh[u * 16 + j]) - mx);
                 }
+                xch[(4 + hh) * TILE_M + row] = sum;
+                epi_barrier();
+                sum += xch[(4 + (hh ^ 1)) * TILE_M + row];
                 const float lse = logf(sum);
-                // tree mode: logits -> half -> exp table -> pi row + row summary, straight into the search tree (what
+                // pass 3 — tree mode: logits -> half -> exp table -> pi row + row summary, straight into the search tree (what
                 // bl_tree_set_eval does for injected evaluations); otherwise fp32 logits / v for the caller
                 const int nd = sv >> 8;
                 const size_t slot = p.tree_mode && live ? (size_t)m * p.tree.T + nd : 0;
                 float pmax = 0.f, pmin = BL_INF_F;
                 int fz = 255, lz = -1;
-                for (int c0 = 0; c0 < Np; c0 += 32) {
-                    uint32_t acc[32];
-                    tmem_ld32(tmem + lane_base + c0, acc);
-                    tmem_wait_ld();
+                for (int u = u_begin; u < u_end; u++) {
+                    uint32_t acc[16];
+                    ld16(u, acc);
+                    const uint32_t vb = bits16(u);
                     if (live) {
-                        int r = c0 / S, c = c0 - r * S;
+                        float lg[16];
 #pragma unroll
-                        for (int j0 = 0; j0 < 32; j0 += 4) {
-                            float out[4];
+                        for (int j = 0; j < 16; j++)
+                            lg[j] = ((vb >> j) & 1u) ? ((__uint_as_float(acc[j]) + bh[u * 16 + j]) - mx) - lse : -BL_INF_F;
+                        if (p.tree_mode) {
+                            float pv[16];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const int a = c0 + j0 + u;
-                                float lg = -BL_INF_F;
-                                if (a < A && brow[seat ? c * S + r : a] == BL_EMPTY) lg = ((__uint_as_float(acc[j0 + u]) + bh[a]) - mx) - lse;
-                                if (p.tree_mode) {
-                                    const bl_half hl = bl_f2h(lg);
-                                    float pv = a < A ? p.tree.exp_lut[hl] : 0.f;
-                                    if (a < A && p.tree.logits) p.tree.logits[slot * A + a] = hl;
-                                    if (pv != 0.f) { pmax = fmaxf(pmax, pv); pmin = fminf(pmin, pv); fz = min(fz, a); lz = max(lz, a); }
-                                    out[u] = pv;
-                                } else if (a < A) p.logits[(size_t)m * A + a] = lg;
-                                if (++c == S) { c = 0; r++; }
+                            for (int j = 0; j < 16; j++) {             // 16 independent table look-ups in flight
+                                const int a = u * 16 + j;
+                                const bl_half hl = bl_f2h(lg[j]);
+                                pv[j] = ((vb >> j) & 1u) ? p.tree.exp_lut[hl] : 0.f;     // exp(-inf) = 0 for illegal / padding columns
+                                if (a < A && p.tree.logits) p.tree.logits[slot * A + a] = hl;
                             }
-                            if (p.tree_mode && c0 + j0 < p.tree.AP)
-                                *reinterpret_cast<float4 *>(p.tree.pi + slot * p.tree.AP + c0 + j0) = make_float4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                const int a = u * 16 + j;
+                                if (pv[j] != 0.f) { pmax = fmaxf(pmax, pv[j]); pmin = fminf(pmin, pv[j]); fz = min(fz, a); lz = max(lz, a); }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                if (u * 16 + j < p.tree.AP)
+                                    *reinterpret_cast<float4 *>(p.tree.pi + slot * p.tree.AP + u * 16 + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                if (u * 16 + j < A) p.logits[(size_t)m * A + u * 16 + j] = lg[j];
                         }
                     }
                 }
-                if (live) {
-                    const float v0 = seat ? -tanh_v : tanh_v, v1 = -v0;
-                    if (p.tree_mode) {
+                if (p.tree_mode) {
+                    // row summary: combine the two warps' partial (max, min, first, last)
+                    xch[(6 + hh) * TILE_M + row] = pmax;
+                    xch[(8 + hh) * TILE_M + row] = pmin;
+                    xch[(10 + hh) * TILE_M + row] = __int_as_float(fz | (lz < 0 ? 0xFFFF00 : lz << 8));
+                    epi_barrier();
+                    if (hh == 0 && live) {
+                        pmax = fmaxf(pmax, xch[7 * TILE_M + row]);
+                        pmin = fminf(pmin, xch[9 * TILE_M + row]);
+                        const int o = __float_as_int(xch[11 * TILE_M + row]);
+                        fz = min(fz, o & 255);
+                        const int olz = (o >> 8) == 0xFFFF ? -1 : (o >> 8);
+                        lz = max(lz, olz);
+                        const float v0 = seat ? -tanh_v : tanh_v, v1 = -v0;
                         uint32_t *ax = reinterpret_cast<uint32_t *>(p.tree.aux + slot);
                         ax[1] = (uint32_t)bl_f2h(v0) | ((uint32_t)bl_f2h(v1) << 16);
                         reinterpret_cast<uint2 *>(ax)[1] = make_uint2(__float_as_uint(pmax), (__float_as_uint(pmin) >> 16) | ((uint32_t)(fz & 255) << 16) |
                                                                                                    ((uint32_t)((lz < 0 ? 0 : lz) & 255) << 24));
-                    } else {
-                        p.v[(size_t)m * 2] = v0;
-                        p.v[(size_t)m * 2 + 1] = v1;
                     }
+                } else if (hh == 0 && live) {
+                    const float v0 = seat ? -tanh_v : tanh_v;
+                    p.v[(size_t)m * 2] = v0;
+                    p.v[(size_t)m * 2 + 1] = -v0;
                 }
             }
             tc_fence_before();
+            TCK(4);
         }
+        if (p.prof && threadIdx.x == 0) for (int k = 0; k < 6; k++) atomicAdd(p.prof + 20 + k, (unsigned long long)pc[k]);
     }
     tc_fence_before();
     __syncthreads();
@@ -474,15 +550,18 @@ int launch(const bl_fc_params *p, TcParams &k, int B, cudaStream_t st) {
     const int S = p->S, A = S * S, W = p->W;
     k.blob = reinterpret_cast<const uint8_t *>(p->packed);
     k.cbias = p->b_head;
+    k.prof = bl_phase_prof();
     k.B = B; k.S = S; k.A = A; k.W = W; k.D = p->D; k.precision = p->precision;
     k.K0p = (2 * A + KC - 1) / KC * KC;
     k.Np = (A + 1 + 31) / 32 * 32;
-    const Shape sh = make_shape(W, k.K0p, k.Np);
+    k.nsplit = p->tc_nsplit == 2 ? 2 : 1;
+    const Shape sh = make_shape(W, k.K0p, k.Np, k.nsplit);
     int ns = MAX_STAGES;
-    while (ns >= 2 && smem_bytes(sh, ns, A) > 227 * 1024) ns--;
+    const size_t extra = bias_bytes(W, p->D, k.Np);
+    while (ns >= 2 && smem_bytes(sh, ns, A) + extra > 227 * 1024) ns--;
     if (ns < 2) return -2;
     k.nstages = ns;
-    const size_t smem = smem_bytes(sh, ns, A);
+    const size_t smem = smem_bytes(sh, ns, A) + extra;
     cudaError_t e = cudaFuncSetAttribute(fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int ntiles = (B + TILE_M - 1) / TILE_M;

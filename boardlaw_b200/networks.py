@@ -58,6 +58,9 @@ class FCModel(nn.Module):
         self._pack = None
         # False routes every shape through the CUDA-core fp32 kernels (net.cu) — used as the on-device cross-check
         self.tensor_cores = True
+        # tile order of the packed operands (bl_fc_params.tc_nsplit); BL_TC_NSPLIT overrides for experiments
+        import os
+        self.tc_nsplit = int(os.environ.get('BL_TC_NSPLIT', '1'))
 
     def sampler(self, logits, test=False):
         if test:
@@ -83,9 +86,9 @@ class FCModel(nn.Module):
                 w_val=f(self.value.core.weight).reshape(-1), b_val=f(self.value.core.bias).reshape(-1))
             tc = {}
             if self.tensor_cores and W in (32, 64, 128, 256) and self.boardsize ** 2 + 1 <= 256:
-                blob, b_head = pack_tensor_core_operands(pack, self.boardsize)
+                blob, b_head = pack_tensor_core_operands(pack, self.boardsize, self.tc_nsplit)
                 pack['packed'], pack['b_head'] = blob, b_head
-                tc = dict(packed=blob.data_ptr(), b_head=b_head.data_ptr())
+                tc = dict(packed=blob.data_ptr(), b_head=b_head.data_ptr(), tc_nsplit=self.tc_nsplit)
             cp = _lib.FCParams(
                 S=self.boardsize, W=W, D=len(res), precision=0 if self.precision == 'fp32' else 1,
                 **{k: t.data_ptr() for k, t in pack.items() if k not in ('packed', 'b_head')}, **tc)
@@ -133,7 +136,7 @@ def _split_tiles(w, n_pad, k_pad):
     return t.permute(3, 0, 1, 4, 2, 5).contiguous()                      # (chunk, 2, n/8, k/8, n%8, k%8)
 
 
-def pack_tensor_core_operands(pack, boardsize):
+def pack_tensor_core_operands(pack, boardsize, nsplit=1):
     """The weight blob fc_tc_kernel streams, in the kernel's consumption order (net_tc.cu): per layer the four blocks
     (N half 0, K half 0), (N half 1, K half 0), (N half 0, K half 1), (N half 1, K half 1) — one block when W < 64 — then the
     fused head [policy ; value]; every weight split as hi = fp16(w), lo = fp16(w - hi).  The ReZero gate is folded into the
@@ -143,7 +146,7 @@ def pack_tensor_core_operands(pack, boardsize):
     W = pack['w_in'].shape[0]
     k0p = (2 * A + KC - 1) // KC * KC
     n_p = (A + 1 + 31) // 32 * 32
-    nh = 2 if W >= 64 else 1
+    nh = 2 if (nsplit == 2 and W >= 64) else 1
     wh = W // nh
 
     def body(w, k_pad):

@@ -131,6 +131,8 @@ typedef struct bl_fc_params {
                              boardlaw_b200/networks.py:pack_tensor_core_operands; NULL: CUDA-core path              */
     const float *b_head;  /* with `packed`: (D+1, W) cumulative biases c_0 = b_in, c_k = c_{k-1} + alpha_k b_k, then
                              (roundup(A+1,32),) = [policy bias (A), value bias, zeros]                              */
+    int tc_nsplit;        /* how `packed` orders a layer's tiles: 1 = whole-N tiles in K order, 2 = the four (N half, K half)
+                             blocks of net_tc.cu (lets the epilogue overlap the MMAs; N = W/2 per instruction)      */
 } bl_fc_params;
 
 /* 1 when bl_fc_forward / bl_tree_eval_leaves run this shape on the tcgen05 kernel (W in {32,64,128,256}, packed operands
@@ -222,9 +224,11 @@ int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint
  * Both produce identical results. */
 int bl_debug_set_descend_variant(int variant);
 
-/* Phase clock of the descent kernel: when `buf` (16 x uint64 on the device, zeroed by the caller) is non-NULL every warp adds the
+/* Phase clock of the descent and network kernels: when `buf` (32 x uint64 on the device, zeroed by the caller) is non-NULL every warp adds the
  * cycles it spent per phase — [0] loop head, [1] sample+advance, [2] finish/fetch, [3] visit, [4] child terms, [5] pass,
- * [6] Newton update/tail, [7..10] visit sub-phases — and [15] += 1.  NULL (default) switches it off. */
+ * [6] Newton update/tail, [7..10] visit sub-phases — and [15] += 1; the network kernel's MMA thread adds [16] wait for operand,
+ * [17] wait for weights, [18] issue, its first epilogue thread [20] board staging, [21] one-hot operand, [22] wait for accumulator,
+ * [23] layer epilogue, [24] heads, [25] wait for heads — and [31] += 1 per CTA.  NULL (default) switches it off. */
 int bl_debug_set_phase_profile(uint64_t *buf);
 
 /* Self test: counts operand pairs for which the shared-reciprocal division of descend.cu differs from the IEEE

@@ -21,7 +21,7 @@ eng = engine_for(worlds, T)
 cp = net.packed()
 names = ['head', 'sample+advance', 'finish/fetch', 'visit: rest (child tops, state)', 'child terms', 'pass', 'newton/tail', 'visit: loads issued + parent scan', 'visit: cp.async wait', 'visit: adopt children', 'visit: lambda + scale row', '-']
 for label, prof_on in (('plain', False), ('clocked', True)):
-    buf = torch.zeros(16, dtype=torch.int64, device='cuda')
+    buf = torch.zeros(32, dtype=torch.int64, device='cuda')
     _lib.lib().bl_debug_set_phase_profile(_lib.ptr(buf) if prof_on else None)
     eng.reset(worlds.board, worlds.seats, 1 / 16)
     eng.eval_root(cp)
@@ -41,4 +41,9 @@ for label, prof_on in (('plain', False), ('clocked', True)):
         print(f'warps x launches = {nw}; avg cycles per warp per launch = {tot / nw:.0f}')
         for k, n in enumerate(names):
             print(f'  {n:16s} {c[k] / nw:9.0f} cycles  {100 * c[k] / tot:5.1f}%')
+        ncta = max(c[31], 1)
+        print(f'network kernel: CTAs x launches = {ncta}')
+        for k, n in ((16, 'mma: wait operand'), (17, 'mma: wait weights'), (18, 'mma: issue'), (20, 'epi: board staging'), (21, 'epi: one-hot operand'),
+                     (22, 'epi: wait accumulator'), (23, 'epi: layer epilogue'), (24, 'epi: heads'), (25, 'epi: wait heads')):
+            print(f'  {n:24s} {c[k] / ncta:9.0f} cycles per CTA per launch')
 _lib.lib().bl_debug_set_phase_profile(None)
