@@ -404,68 +404,57 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
 }
 
 // ---- expand + env step (boardlaw/mcts/__init__.py:117-129), one lane per env ---------------------------------------------------
-constexpr int XNT = 64;
-constexpr int XPITCH = XNT + 4;
+// Each lane moves its parent's board (BP bytes, 16-byte loads) into a lane-private shared-memory row with an odd word pitch,
+// places the stone / relabels the group there, and writes the row to the leaf's slot with 16-byte stores.
+constexpr int XNT = 128;
 
 __global__ void __launch_bounds__(XNT) expand_step_kernel(bl_tree t, int sim) {
     extern __shared__ __align__(16) uint8_t raw[];
-    uint8_t *bd = raw, *stk = raw + (size_t)t.A * XPITCH;
-    const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-    const int A = t.A, T = t.T;
-    const int b = blockIdx.x * XNT + tid, bw = blockIdx.x * XNT + wbase;
-    const bool in_range = b < t.B;
-    const size_t node0 = (size_t)(in_range ? b : 0) * T;
-    int leaf = -1, parent = 0, action = -1;
-    bool ok = false, fresh = false;
-    bl_node pn, ln;
-    if (in_range) {
-        leaf = t.leaf[b]; parent = t.leaf_parent[b]; action = t.leaf_action[b];
-        ok = action >= 0;
-        if (ok) {
-            pn = bl_ld_node(t.node + node0 + parent);
-            if (leaf < 0) {                                     // new node in slot `sim`
-                leaf = sim;
-                fresh = true;
-                ln.parent = (int16_t)parent; ln.relation = (int16_t)action; ln.first_child = -1; ln.next_sib = pn.first_child;
-                ln.n = 0; ln.w[0] = 0; ln.w[1] = 0;
-                t.node[node0 + parent].first_child = (int16_t)sim;
-                t.parent_of[(size_t)b * ((T + 7) & ~7) + sim] = (int16_t)parent;
-            } else {                                            // stopped at an existing terminal child: reuse its slot
-                ln = bl_ld_node(t.node + node0 + leaf);
-            }
-        } else {
-            leaf = -1;
-            atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_ERRORS), 1ull);
-        }
+    const int tid = threadIdx.x;
+    const int T = t.T, nq = t.BP >> 4, pw = (t.BP >> 2) | 1;       // 16-byte pieces per board, row pitch in words (odd)
+    uint32_t *bdw = reinterpret_cast<uint32_t *>(raw) + (size_t)tid * pw;
+    uint8_t *bd = reinterpret_cast<uint8_t *>(bdw);
+    uint8_t *stk = raw + (size_t)XNT * pw * 4 + (size_t)tid * pw * 4;
+    const int b = blockIdx.x * XNT + tid;
+    if (b >= t.B) return;
+    const size_t node0 = (size_t)b * T;
+    int leaf = t.leaf[b];
+    const int parent = t.leaf_parent[b], action = t.leaf_action[b];
+    if (action < 0) {
+        t.leaf[b] = -1;
+        atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_ERRORS), 1ull);
+        return;
+    }
+    const uint4 *src = reinterpret_cast<const uint4 *>(t.board + (node0 + parent) * t.BP);
+    for (int i = 0; i < nq; i++) {
+        const uint4 v = src[i];
+        bdw[4 * i] = v.x; bdw[4 * i + 1] = v.y; bdw[4 * i + 2] = v.z; bdw[4 * i + 3] = v.w;
+    }
+    const bl_node pn = bl_ld_node(t.node + node0 + parent);
+    bl_node ln;
+    bool fresh = false;
+    if (leaf < 0) {                                             // new node in slot `sim`
+        leaf = sim;
+        fresh = true;
+        ln.parent = (int16_t)parent; ln.relation = (int16_t)action; ln.first_child = -1; ln.next_sib = pn.first_child;
+        ln.n = 0; ln.w[0] = 0; ln.w[1] = 0;
+        t.node[node0 + parent].first_child = (int16_t)sim;
+        t.parent_of[(size_t)b * ((T + 7) & ~7) + sim] = (int16_t)parent;
         t.leaf[b] = (int16_t)leaf;
+    } else {                                                    // stopped at an existing terminal child: reuse its slot
+        ln = bl_ld_node(t.node + node0 + leaf);
     }
-    const unsigned omask = __ballot_sync(FULL, ok);
-    for (unsigned m = omask; m; m &= m - 1) {
-        const int l = __ffs(m) - 1;
-        const int pl = __shfl_sync(FULL, parent, l);
-        const uint8_t *row = t.board + ((size_t)(bw + l) * T + pl) * t.BP;
-        for (int c = lane; c < A; c += 32) bd[c * XPITCH + wbase + l] = row[c];
-    }
-    __syncwarp();
-    if (ok) {
-        const int seat = pn.seat;
-        const int win = bl_hex_place<uint8_t>(bd + tid, stk + tid, XPITCH, t.S, seat, action);
-        const float r0 = win == 1 ? 1.f : (win == 2 ? -1.f : 0.f), r1 = win == 1 ? -1.f : (win == 2 ? 1.f : 0.f);
-        reinterpret_cast<uint32_t *>(t.aux + node0 + leaf)[0] = (uint32_t)bl_f2h(r0) | ((uint32_t)bl_f2h(r1) << 16);
-        ln.terminal = win != 0;
-        ln.seat = win ? 0 : (uint8_t)(1 - seat);
-        if (fresh) bl_st_node(t.node + node0 + leaf, ln);
-        else bl_st_node_stats(t.node + node0 + leaf, ln);
-        if (win)
-            for (int c = 0; c < A; c++) bd[c * XPITCH + tid] = 0;      // auto-reset (hex/__init__.py:185-188)
-    }
-    __syncwarp();
-    for (unsigned m = omask; m; m &= m - 1) {
-        const int l = __ffs(m) - 1;
-        const int ll = __shfl_sync(FULL, leaf, l);
-        uint8_t *row = t.board + ((size_t)(bw + l) * T + ll) * t.BP;
-        for (int c = lane; c < A; c += 32) row[c] = bd[c * XPITCH + wbase + l];
-    }
+    const int seat = pn.seat;
+    const int win = bl_hex_place<uint8_t>(bd, stk, 1, t.S, seat, action);
+    const float r0 = win == 1 ? 1.f : (win == 2 ? -1.f : 0.f), r1 = win == 1 ? -1.f : (win == 2 ? 1.f : 0.f);   // +0, never -0
+    reinterpret_cast<uint32_t *>(t.aux + node0 + leaf)[0] = (uint32_t)bl_f2h(r0) | ((uint32_t)bl_f2h(r1) << 16);
+    ln.terminal = (uint8_t)win;                                 // 0, or the winner's code (1 = seat 0, 2 = seat 1): the backup
+    ln.seat = win ? 0 : (uint8_t)(1 - seat);                    // reads the rewards (+-1) off it
+    if (fresh) bl_st_node(t.node + node0 + leaf, ln);
+    else bl_st_node_stats(t.node + node0 + leaf, ln);
+    uint4 *dst = reinterpret_cast<uint4 *>(t.board + (node0 + leaf) * t.BP);
+    for (int i = 0; i < nq; i++)                                // a won game auto-resets to the empty board (hex/__init__.py:185-188)
+        dst[i] = win ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(bdw[4 * i], bdw[4 * i + 1], bdw[4 * i + 2], bdw[4 * i + 3]);
 }
 
 // ---- self test of the shared-reciprocal division -----------------------------------------------------------------------------
@@ -540,7 +529,7 @@ extern "C" int64_t bl_tree_scratch_bytes(const bl_tree *t) {
 }
 
 int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st) {
-    const size_t xsmem = (size_t)2 * t->A * XPITCH;
+    const size_t xsmem = (size_t)2 * XNT * ((t->BP >> 2) | 1) * 4;
     if (xsmem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(expand_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsmem);
         if (e != cudaSuccess) return (int)e;

@@ -188,61 +188,76 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
 }
 
 // ---- backup + q-range scan ----------------------------------------------------------------------------------------
-// One CTA per 32 envs: warp 0 walks the 32 leaf->root paths (one 2 x 128-bit load per step), then all warps scan the CTA's
-// 32*T node records for the (min,max) of w/(n+1e-4) that the NEXT descent normalises with (slot sim+1).
-constexpr int BK_ENVS = 32, BK_THREADS = 128;
-__global__ void __launch_bounds__(BK_THREADS) backup_kernel(bl_tree t, int sim) {
-    const int T = t.T;
-    const int b0 = blockIdx.x * BK_ENVS;
-    if (threadIdx.x < BK_ENVS) {
-        const int b = b0 + threadIdx.x;
-        unsigned visited = 0;
-        if (b < t.B) {
-            const size_t base = (size_t)b * T;
-            int cur = t.leaf[b];
-            float val[2] = {0.f, 0.f};
-            bl_node nd;
-            bl_aux ax;
-            if (cur >= 0) {
-                nd = bl_ld_node(t.node + base + cur);
-                ax = bl_ld_aux(t.aux + base + cur);
+// One warp per env: the env's node records 0..sim (16 B each, contiguous) are staged in shared memory with coalesced loads,
+// lane 0 walks the leaf->root path there (shared-memory latency per step instead of a DRAM round trip), the touched records
+// are written back, and the same staged records feed the (min,max) of w/(n+1e-4) that the NEXT descent normalises with
+// (slot sim+1).  Rewards are +-1 for the winner's code stored in the record's `terminal` byte (0 = not terminal).
+constexpr int BK_WARPS = 8;
+__global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int sim, int warps) {
+    extern __shared__ uint4 bsm[];
+    __shared__ int red[2 * BK_WARPS];
+    const int T = t.T, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * warps + warp;
+    const int nrec = sim + 1;                                   // node slots that can be populated so far
+    uint4 *rec = bsm + (size_t)warp * (T + ((T + 31) >> 5));    // T records, then a dirty bitmask (one word per 32 nodes)
+    uint32_t *dirty = reinterpret_cast<uint32_t *>(rec + T);
+    float lo = BL_INF, hi = -BL_INF;
+    unsigned visited = 0;
+    if (b < t.B) {
+        uint4 *g = reinterpret_cast<uint4 *>(t.node + (size_t)b * T);
+        for (int k = lane; k < nrec; k += 32) rec[k] = g[k];
+        for (int k = lane; k < ((T + 31) >> 5); k += 32) dirty[k] = 0;
+        int leaf = -1;
+        float val[2] = {0.f, 0.f};
+        if (lane == 0) {
+            leaf = t.leaf[b];
+            if (leaf >= 0) {
+                const bl_aux ax = bl_ld_aux(t.aux + (size_t)b * T + leaf);
                 val[0] = bl_h2f(ax.v[0]); val[1] = bl_h2f(ax.v[1]);
             }
-            while (cur >= 0) {
-                const int next = nd.parent;
-                bl_node pn;
-                bl_aux pa;
-                if (next >= 0) { pn = bl_ld_node(t.node + base + next); pa = bl_ld_aux(t.aux + base + next); }   // in flight during the update
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int cur = leaf; cur >= 0;) {
+                union { uint4 u; bl_node n; } x;
+                x.u = rec[cur];
+                const float r0 = x.n.terminal == 1 ? 1.f : (x.n.terminal == 2 ? -1.f : 0.f);
+                const float rw[2] = {r0, x.n.terminal == 1 ? -1.f : (x.n.terminal == 2 ? 1.f : 0.f)};      // +0, never -0
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
-                    if (nd.terminal) val[s] = 0.f;
-                    val[s] = __fadd_rn(val[s], bl_h2f(ax.rewards[s]));
-                    nd.w[s] = bl_f2h(__fadd_rn(bl_h2f(nd.w[s]), bl_h2f(bl_f2h(val[s]))));
+                    if (x.n.terminal) val[s] = 0.f;
+                    val[s] = __fadd_rn(val[s], rw[s]);
+                    x.n.w[s] = bl_f2h(__fadd_rn(bl_h2f(x.n.w[s]), bl_h2f(bl_f2h(val[s]))));
                 }
-                nd.n = (int16_t)(nd.n + t.Sn);                      // quirk: +1 per seat (cuda.cu:228)
-                bl_st_node_stats(t.node + base + cur, nd);
-                cur = next; nd = pn; ax = pa;
+                x.n.n = (int16_t)(x.n.n + t.Sn);                    // quirk: +1 per seat (cuda.cu:228)
+                rec[cur] = x.u;
+                dirty[cur >> 5] |= 1u << (cur & 31);
+                cur = x.n.parent;
                 visited++;
             }
         }
-        bl_count(t.counters, C_BACKUP_NODES, visited);
-    }
-    __syncthreads();
-    const int nb = min(BK_ENVS, t.B - b0);
-    const bl_node *first = t.node + (size_t)b0 * T;
-    float lo = BL_INF, hi = -BL_INF;
-    for (int i = threadIdx.x; i < nb * T; i += BK_THREADS) {
-        const bl_node nd = bl_ld_node(first + i);
-        const float q0 = bl_qraw(nd.w[0], nd.n), q1 = bl_qraw(nd.w[1], nd.n);
-        lo = fminf(lo, fminf(q0, q1));
-        hi = fmaxf(hi, fmaxf(q0, q1));
+        __syncwarp();
+        for (int k = lane; k < nrec; k += 32) {
+            union { uint4 u; bl_node n; } x;
+            x.u = rec[k];
+            if ((dirty[k >> 5] >> (k & 31)) & 1u) reinterpret_cast<uint2 *>(g + k)[1] = make_uint2(x.u.z, x.u.w);   // (n, w, seat, terminal)
+            const float q0 = bl_qraw(x.n.w[0], x.n.n), q1 = bl_qraw(x.n.w[1], x.n.n);
+            lo = fminf(lo, fminf(q0, q1));
+            hi = fmaxf(hi, fmaxf(q0, q1));
+        }
+        if (nrec < T) { lo = fminf(lo, 0.f); hi = fmaxf(hi, 0.f); }     // untouched slots: w = 0, n = 0 -> q = 0
     }
     const int klo = __reduce_min_sync(0xffffffffu, bl_f2ord(lo)), khi = __reduce_max_sync(0xffffffffu, bl_f2ord(hi));
-    if (bl_lane() == 0) {
+    if (lane == 0) { red[warp] = klo; red[BK_WARPS + warp] = khi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = red[0], c = red[BK_WARPS];
+        for (int w = 1; w < warps; w++) { a = min(a, red[w]); c = max(c, red[BK_WARPS + w]); }
         int *qr = reinterpret_cast<int *>(t.qrange) + 2 * (sim + 1);
-        atomicMin(qr, klo);
-        atomicMax(qr + 1, khi);
+        atomicMin(qr, a);
+        atomicMax(qr + 1, c);
     }
+    if (lane == 0 && visited) atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_BACKUP_NODES), (unsigned long long)visited);
 }
 
 // ---- root ------------------------------------------------------------------------------------------------------------
@@ -387,7 +402,17 @@ extern "C" int bl_tree_backup(const bl_tree *t, int sim, bl_stream stream) {
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (sim < 1 || sim >= t->T) return -1;
-    backup_kernel<<<(t->B + BK_ENVS - 1) / BK_ENVS, BK_THREADS, 0, bl_cu(stream)>>>(*t, sim);
+    // warps (= envs) per CTA: as many as fit in shared memory, at most BK_WARPS
+    const size_t per_warp = ((size_t)t->T + ((t->T + 31) >> 5)) * sizeof(uint4);
+    int warps = (int)(200 * 1024 / per_warp);
+    if (warps < 1) return -2;
+    if (warps > BK_WARPS) warps = BK_WARPS;
+    const size_t smem = per_warp * warps;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(backup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    backup_kernel<<<(t->B + warps - 1) / warps, warps * 32, smem, bl_cu(stream)>>>(*t, sim, warps);
     BL_LAUNCH_CHECK();
 }
 

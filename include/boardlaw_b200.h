@@ -162,7 +162,7 @@ typedef struct bl_node {
     int16_t n;            /* visit count (incremented Sn per visit, as the reference)               */
     bl_half w[2];         /* accumulated value per seat                                             */
     uint8_t seat;         /* seat to move                                                           */
-    uint8_t terminal;
+    uint8_t terminal;     /* 0, or the code of the seat whose move ended the game here (1 = seat 0, 2 = seat 1)  */
 } bl_node;
 
 /* Second 16-byte record per (env, node): what only the backup and the row load need. */
