@@ -100,6 +100,20 @@ def algorithmic_bytes(S, T, counters, n_desc):
     return {'descend_expand': descend + expand_step, 'net': net_io, 'backup': backup}
 
 
+def ncu_traffic(kind):
+    """dram read + write bytes per launch of the dominant kernel, from the committed ``ncu --set full`` summary (profiles/)."""
+    name = {'descend_expand': 'r01_descend_v3_ncu_full.txt', 'net': 'r01_fc_tc_ncu_full.txt'}.get(kind)
+    f = ROOT / 'profiles' / name if name else None
+    if not f or not f.exists():
+        return None
+    total, scale = 0., {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for line in f.read_text().splitlines():
+        if line.startswith('dram__bytes_read.sum [') or line.startswith('dram__bytes_write.sum ['):
+            unit = line.split('[')[1].split(']')[0]
+            total += float(line.split('=')[1]) * scale.get(unit, 1)
+    return total or None
+
+
 def net_flops(S, W, D):
     A = S * S
     return 2 * (2 * A * W + D * W * W + W * A + W)
@@ -254,12 +268,14 @@ def run_ours(args):
             flops = net_flops(S, W, D) * n_desc
             achieved = flops / (split['net'] / 1e3) / 1e12
             roofline = {'kernel': 'fc_forward (leaf evaluation)', 'bound': 'tensor', 'achieved': achieved, 'peak': tc_peak,
-                        'unit': 'TFLOP/s', 'frac': achieved / tc_peak, 'traffic': None,
+                        'unit': 'TFLOP/s', 'frac': achieved / tc_peak, 'traffic': ncu_traffic('net'),
                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback'}
         else:
             achieved = bytes_by[dominant] / (split[dominant] / 1e3) / 1e9
             roofline = {'kernel': dominant, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                        'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': hbm_src}
+                        'frac': achieved / hbm_peak, 'traffic': ncu_traffic(dominant), 'peak_source': hbm_src,
+                        'note': 'bytes are SURVEY 8(d) algorithmic bytes; the descent is a chain of dependent fp32 additions in the '
+                                'reference order (bit-exact parity), bounded by fp32-pipe issue and latency, not by HBM (DESIGN.md 5.1)'}
         roofline['ms_per_move_by_kernel'] = {k: round(v, 3) for k, v in split.items()}
         roofline['launches_per_move_by_kernel'] = per_move_launches
         roofline['algorithmic_bytes_per_move'] = {k: int(v) for k, v in bytes_by.items()}

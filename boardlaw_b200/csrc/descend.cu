@@ -21,6 +21,9 @@
 //     when the pass turns out to be the last one.
 //
 // Compiled with -fmad=false -prec-div=true -ftz=false (see build.py); fused operations are explicit.
+#include <cstdio>
+#include <cstdlib>
+
 #include "engine_internal.cuh"
 #include "hex_core.cuh"
 #include "mcts_core.cuh"
@@ -49,12 +52,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // latency on every trip
 #ifndef BL_GATE_NUM
 #define BL_GATE_NUM 1
-#define BL_GATE_DEN 3
+#define BL_GATE_DEN 2      /* measured on c2: 1/2 17.3 ms, 1/3 18.5, 2/3 18.4, 1/4 19.6, every trip 23.4 ms per move */
 #endif
 
 template <int NCH, bool PROF>
 __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_t seed,
-                                                        ChildEntry *__restrict__ clists, int cap, unsigned long long *prof) {
+                                                        ChildEntry *__restrict__ clists, int cap, unsigned long long *prof,
+                                                        int gate_num, int gate_den) {
     constexpr int PS = 4 * NCH;                         // row pitch in floats; NCH odd => conflict-free 128-bit lane-private rows
     constexpr int KS = NCH;                             // child entries (16 B each) kept in the lane's shared-memory row (rest: global scratch)
     constexpr int NW = (PS + 63) / 64;                  // 64-bit words of the child-position mask
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
         if (livem == 0) break;
         tick(0);
         const unsigned needm = livem & ~passm;
-        if (passm == 0 || __popc(needm) * BL_GATE_DEN >= __popc(livem) * BL_GATE_NUM) {
+        if (passm == 0 || __popc(needm) * gate_den >= __popc(livem) * gate_num) {
             // ---- G: inverse-CDF search over the running sums (descend_kernel, cuda.cu:160-176) ----------------------------------
             if (state == ST_SAMPLE) {
                 // every term is >= 0 (checked for child terms in C), so the sums are non-decreasing: first index with sum >= r.
@@ -494,6 +498,17 @@ __global__ void __launch_bounds__(256) divtest_kernel(uint64_t seed, int n_div, 
 }
 
 unsigned long long *g_phase_prof = nullptr;
+// service gate (see the kernel): BL_GATE="num/den" in the environment overrides the default for tuning runs
+int g_gate_num = BL_GATE_NUM, g_gate_den = BL_GATE_DEN;
+void read_gate_env() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (const char *e = getenv("BL_GATE")) {
+        int a = 0, b = 0;
+        if (sscanf(e, "%d/%d", &a, &b) == 2 && a >= 0 && b > 0) { g_gate_num = a; g_gate_den = b; }
+    }
+}
 
 template <int NCH, bool PROF>
 int launch_v3p(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, int cap, cudaStream_t st) {
@@ -511,7 +526,8 @@ int launch_v3p(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, i
     const int need = (t->B + 31) / 32;
     const int grid = need < occ * BL_NUM_SMS ? need : occ * BL_NUM_SMS;
     if ((int64_t)grid * 32 * cap * (int64_t)sizeof(ChildEntry) > t->scratch_bytes) return -3;
-    descend_v3_kernel<NCH, PROF><<<grid, 32, smem, st>>>(*t, sim, rands, seed, reinterpret_cast<ChildEntry *>(t->scratch), cap, g_phase_prof);
+    descend_v3_kernel<NCH, PROF><<<grid, 32, smem, st>>>(*t, sim, rands, seed, reinterpret_cast<ChildEntry *>(t->scratch), cap, g_phase_prof,
+                                                         g_gate_num, g_gate_den);
     return (int)cudaGetLastError();
 }
 template <int NCH>
@@ -539,6 +555,7 @@ int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st) {
 }
 
 int bl_descend_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st) {
+    read_gate_env();
     const int cap = child_cap(t);
     const int nch = (t->A + 3) / 4;
     cudaError_t e = cudaMemsetAsync(t->counters + C_QUEUE, 0, sizeof(uint64_t), st);

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+nvidia-smi -L > gpurun_out/gpus.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_2gpu.log 2>&1
+tail -c 3000 gpurun_out/bench_2gpu.log
