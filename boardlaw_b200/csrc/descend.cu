@@ -33,9 +33,9 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 #define BL_TINY 7.888609052210118e-31f   /* 2^-100 */
 
-enum { ST_IDLE = 0, ST_VISIT = 1, ST_PASS = 2, ST_FINAL = 3, ST_SAMPLE = 4, ST_SLOW = 5, ST_ADVANCE = 6 };
+enum { ST_IDLE = 0, ST_VISIT = 1, ST_PASS = 2, ST_FINAL = 3, ST_SAMPLE = 4, ST_SLOW = 5, ST_ADVANCE = 6, ST_DONE = 7 };
 
-struct __align__(16) ChildEntry { float q, top; int a, id; };
+struct __align__(16) ChildEntry { float q, top; int a, id, flags; };   // flags: seat | terminal << 8 of the child (shared-memory form packs a|id and flags)
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float a, float b) { return ((u64)__float_as_uint(b) << 32) | __float_as_uint(a); }
@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                                                         ChildEntry *__restrict__ clists, int cap, unsigned long long *prof,
                                                         int gate_num, int gate_den) {
     constexpr int PS = 4 * NCH;                         // row pitch in floats; NCH odd => conflict-free 128-bit lane-private rows
-    constexpr int KS = NCH;                             // child entries (16 B each) kept in the lane's shared-memory row (rest: global scratch)
+    // the lane's third shared-memory row holds its child entries (16 B each; the rest go to global scratch) and, when it fits, a
+    // copy of the env's parent row (scanned at every visit)
     constexpr int NW = (PS + 63) / 64;                  // 64-bit words of the child-position mask
     constexpr int MW = 4;                               // 64-bit words of the children-of-this-node mask (T <= 256; else list walk)
     constexpr int STEP0 = PS >= 128 ? 128 : (PS >= 64 ? 64 : (PS >= 32 ? 32 : (PS >= 16 ? 16 : 8)));
@@ -80,12 +81,16 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
     const int nrow4 = t.AP >> 2;
     const int TP = (T + 7) & ~7;
     const bool scan_ok = T <= 64 * MW;
+    const bool pcache = scan_ok && TP * 2 + 5 * 16 <= PS * 4;      // parent row cached in shared memory, >= 5 entry slots left
+    const int KS = pcache ? (PS * 4 - TP * 2) / 16 : NCH;
+    const uint4 *pc4 = reinterpret_cast<const uint4 *>(pe4 + KS);
+    const uint32_t pc_addr = pe_addr + 16u * KS;
     const int nscan = (sim + 7) >> 3;                 // 16-byte chunks of the parent row that can hold nodes created so far
 
     u64 tp[2 * NCH];                                  // lambda*pi of the current node, element pairs
     u64 cm[NW];                                       // bit a set: action a has a child
-    int b = -1, cur = -1, parent = 0, action = -1, state = ST_VISIT, nc = 0, it = 0;
-    float alpha = 1.f, error = 0.f, r = 0.f;
+    int b = -1, cur = -1, parent = 0, action = -1, state = ST_DONE, nc = 0, it = 0, cur_seat = 0;
+    float alpha = 1.f, error = 0.f, r = 0.f, c_puct = 0.f;
     uint32_t nzpos = 0;                               // first_nz | last_nz << 8 of the current row
     bool exhausted = false;                           // warp-uniform: the queue has nothing left
     const bool all_resident = (long long)gridDim.x * 32 >= t.B;   // every env has a lane: no queue, env = global lane index
@@ -93,10 +98,10 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
 #pragma unroll
     for (int w = 0; w < NW; w++) cm[w] = 0;
     // optional phase clock (bl_debug_set_phase_profile): cycles per phase summed over warps, for DESIGN.md's latency budget
-    long long pc[PROF ? 12 : 1], tlast = PROF ? clock64() : 0;
+    long long pc[PROF ? 13 : 1], tlast = PROF ? clock64() : 0;
 #pragma unroll
-    for (int k = 0; k < (PROF ? 12 : 1); k++) pc[k] = 0;
-#define tick(k) do { if (PROF) { const long long now_ = clock64(); pc[k] += now_ - tlast; tlast = now_; } } while (0)
+    for (int k = 0; k < (PROF ? 13 : 1); k++) pc[k] = 0;
+#define tick(k) do { if (PROF) { __syncwarp(__activemask()); const long long now_ = clock64(); pc[k] += now_ - tlast; tlast = now_; } } while (0)
 
     auto get = [&](int i) {
         ChildEntry e;
@@ -104,12 +109,12 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
             const float4 v = pe4[i];
             e.q = v.x; e.top = v.y;
             const uint32_t u = __float_as_uint(v.z);
-            e.a = u & 255; e.id = u >> 8;
+            e.a = u & 255; e.id = u >> 8; e.flags = __float_as_int(v.w);
         } else e = cl[i];
         return e;
     };
     auto put = [&](int i, const ChildEntry &e) {
-        if (i < KS) pe4[i] = make_float4(e.q, e.top, __uint_as_float((uint32_t)e.a | ((uint32_t)e.id << 8)), 0.f);
+        if (i < KS) pe4[i] = make_float4(e.q, e.top, __uint_as_float((uint32_t)e.a | ((uint32_t)e.id << 8)), __int_as_float(e.flags));
         else cl[i] = e;
     };
 
@@ -118,8 +123,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
     // next service, a trip or more later, so the DRAM latency is spent while the other lanes run their passes.
     auto prefetch_node = [&](int n) {
         const size_t slot = (size_t)b * T + n;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pe_addr), "l"(t.node + slot) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pe_addr + 16u), "l"(t.aux + slot) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pg_addr), "l"(t.aux + slot) : "memory");       // row summary -> pg[0..3]
         const float4 *row = reinterpret_cast<const float4 *>(t.pi + slot * t.AP);
 #pragma unroll
         for (int c = 0; c < NCH; c++)
@@ -149,34 +153,26 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                 action = first_nz == 255 ? -1 : (l < A ? (r <= 0.f ? first_nz : l) : last_nz);
                 state = ST_ADVANCE;
             }
-            // ---- H: step to the chosen child; its data starts travelling now ----------------------------------------------------
+            // ---- H: step to the chosen child (its seat / terminal flag were read with its statistics); its row starts travelling ----
             if (state == ST_ADVANCE) {
                 parent = cur;
-                int next = -1;
+                int next = -1, nflags = 0;
                 for (int i = 0; i < nc; i++) {
                     const ChildEntry e = get(i);
-                    if (e.a == action) next = e.id;
+                    if (e.a == action) { next = e.id; nflags = e.flags; }
                 }
                 cur = action >= 0 ? next : -1;
-                state = ST_VISIT;
-                if (cur >= 0) prefetch_node(cur);
+                if (cur >= 0 && !(nflags >> 8)) { cur_seat = nflags & 255; state = ST_VISIT; prefetch_node(cur); }
+                else state = ST_DONE;                               // new leaf, existing terminal child, or no legal action
             }
             tick(1);
             // ---- A: finished descents write their result and take the next env -------------------------------------------
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            bl_node nd;
-            bool evaluable = false, fresh = false;
-            if (state == ST_VISIT) {
-                if (b >= 0 && cur >= 0) { union { float4 f; bl_node n; } x; x.f = pe4[0]; nd = x.n; evaluable = !nd.terminal; }
-                if (!evaluable) {
-                    if (b >= 0) {
-                        t.leaf[b] = (int16_t)cur;                      // existing terminal child, or -1: expand_step decides
-                        t.leaf_parent[b] = (int16_t)parent;
-                        t.leaf_action[b] = (int16_t)action;
-                        c_desc++;
-                    }
-                    fresh = true;
-                }
+            const bool fresh = state == ST_DONE;
+            if (fresh && b >= 0) {
+                t.leaf[b] = (int16_t)cur;                          // existing terminal child, or -1: expand_step decides
+                t.leaf_parent[b] = (int16_t)parent;
+                t.leaf_action[b] = (int16_t)action;
+                c_desc++;
             }
             const unsigned req = __ballot_sync(FULL, fresh);
             if (req) {
@@ -191,22 +187,31 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                     if (all_resident) nb = (b < 0 && !exhausted) ? (int)blockIdx.x * 32 + lane : t.B;
                     b = nb < t.B ? nb : -1;
                     cur = 0; parent = 0; action = -1;
-                    state = b < 0 ? ST_IDLE : ST_VISIT;
-                    if (b >= 0) prefetch_node(0);
+                    state = ST_IDLE;
+                    if (b >= 0) {
+                        const bl_node root = bl_ld_node_hint(t.node + (size_t)b * T, keep);
+                        c_puct = bl_h2f(t.c_puct[b]);
+                        cur_seat = root.seat;
+                        if (root.terminal) state = ST_DONE;       // a terminal root ends the descent at the next service (leaf = 0, no action)
+                        else {
+                            state = ST_VISIT;
+                            if (pcache) {                          // its own (older) group: the visit waits for it alone first
+                                for (int k = 0; k < (TP >> 3); k++)
+                                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pc_addr + 16u * k),
+                                                 "l"(t.parent_of + (size_t)b * TP + 8 * k) : "memory");
+                                asm volatile("cp.async.commit_group;" ::: "memory");
+                            }
+                            prefetch_node(0);
+                        }
+                    }
                 }
                 if (all_resident) exhausted = true;
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                // a terminal root ends the descent at the next service
-                if (fresh && b >= 0) { union { float4 f; bl_node n; } x; x.f = pe4[0]; nd = x.n; evaluable = !nd.terminal; }
             }
             tick(2);
-            // ---- B: visit — row into registers, child list, N, lambda, random number ------------------------------------------
-            if (state == ST_VISIT && evaluable) {
+            // ---- B: visit — child list, N, lambda, random number, row into registers ------------------------------------------
+            if (state == ST_VISIT) {
                 const size_t node0 = (size_t)b * T;
-                const int seat = nd.seat;
-                bl_aux ax;
-                { union { float4 f; bl_aux a; } x; x.f = pe4[1]; ax = x.a; }
-                const float c_puct = bl_h2f(t.c_puct[b]);
+                const int seat = cur_seat;
                 if (rands) r = bl_h2f(rands[node0 + cur]);
                 else r = bl_uniform_half_grid(bl_philox(seed ^ (move * 0x9E3779B97F4A7C15ull), (uint64_t)b,
                                                         ((uint64_t)sim << 32) | (uint32_t)cur).x);
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                 for (int w = 0; w < NW; w++) cm[w] = 0;
                 auto adopt = [&](const bl_node &ch, int id) {
                     const int a = ch.relation;
-                    put(nc, ChildEntry{qn.fast(seat ? ch.w[1] : ch.w[0], ch.n), ps[a], a, id});      // top: pi for now, scaled below
+                    put(nc, ChildEntry{qn.fast(seat ? ch.w[1] : ch.w[0], ch.n), 0.f, a, id, (int)ch.seat | ((int)ch.terminal << 8)});
                     const u64 bit = 1ull << (a & 63);
 #pragma unroll
                     for (int w = 0; w < NW; w++) cm[w] |= ((a >> 6) == w) ? bit : 0ull;    // (kept in registers: no indexed access)
@@ -227,6 +232,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                     // children = the nodes whose parent is `cur`: one scan of the env's parent row (independent 16-byte loads)
                     // instead of a walk down the sibling list (one dependent load per child); their records are then fetched
                     // together by cp.async straight into the lane's entry slots
+                    if (pcache) asm volatile("cp.async.wait_group 1;" ::: "memory");       // the parent row (older group); the pi row may still fly
                     const uint4 *prow = reinterpret_cast<const uint4 *>(t.parent_of + (size_t)b * TP);
                     const uint32_t cur2 = (uint32_t)cur * 0x10001u;
                     u64 mm[MW];
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
 #pragma unroll
                             for (int j = 0; j < 8; j++) {
                                 if (w * 8 + j < nscan) {
-                                    const uint4 pv = bl_ld16_hint(prow + w * 8 + j, keep);
+                                    const uint4 pv = pcache ? pc4[w * 8 + j] : bl_ld16_hint(prow + w * 8 + j, keep);
                                     const uint32_t e0 = __vcmpeq2(pv.x, cur2), e1 = __vcmpeq2(pv.y, cur2), e2 = __vcmpeq2(pv.z, cur2),
                                                    e3 = __vcmpeq2(pv.w, cur2);
                                     const uint32_t m8 = ((e0 & 1u) | ((e0 >> 15) & 2u)) | (((e1 & 1u) | ((e1 >> 15) & 2u)) << 2) |
@@ -272,6 +278,8 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                             k++;
                         }
                 } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    const bl_node nd = bl_ld_node_hint(t.node + node0 + cur, keep);
                     for (int c = nd.first_child; c >= 0;) {
                         const bl_node ch = bl_ld_node_hint(t.node + node0 + c, keep);
                         adopt(ch, c);
@@ -279,6 +287,8 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                     }
                 }
                 tick(9);
+                bl_aux ax;
+                { union { float4 f; bl_aux a; } x; x.f = reinterpret_cast<const float4 *>(pg)[0]; ax = x.a; }      // landed with the row
                 N += A - nc;                                        // every child-less action counts 1 (cuda.cu:91)
                 const float lambda = bl_lambda(c_puct, N, A);
                 nzpos = (uint32_t)ax.first_nz | ((uint32_t)ax.last_nz << 8);
@@ -296,14 +306,16 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                 const bool tiny = __fmul_rn(lambda, bl_minnz(ax)) < BL_TINY;
                 for (int i = 0; i < nc; i++) {
                     ChildEntry e = get(i);
-                    e.top = __fmul_rn(lambda, e.top);
+                    e.top = __fmul_rn(lambda, ps[e.a]);             // the landed row still holds pi
                     alpha0 = fmaxf(alpha0, __fadd_rn(e.q, fmaxf(e.top, 1.e-4f)));
                     put(i, e);
                 }
                 alpha = alpha0; it = 0; error = BL_INF;
                 state = tiny ? ST_SLOW : ST_PASS;
                 c_evals++; c_children += nc;
+                tick(12);
             }
+            tick(11);
         }
 
         tick(3);
@@ -394,11 +406,15 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
             }
         }
     }
-    if (PROF && lane == 0) {
+    if (PROF) {
         tick(6);
 #pragma unroll
-        for (int k = 0; k < (PROF ? 12 : 1); k++) atomicAdd(prof + k, (unsigned long long)pc[k]);
-        atomicAdd(prof + 15, 1ull);
+        for (int k = 0; k < (PROF ? 13 : 1); k++) {             // per phase: the slowest lane's total (lanes outside a phase hold 0 for it)
+            long long m = pc[k];
+            for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+            if (lane == 0) atomicAdd(prof + k, (unsigned long long)m);
+        }
+        if (lane == 0) atomicAdd(prof + 15, 1ull);
     }
     bl_count(t.counters, C_EVALS, c_evals);
     bl_count(t.counters, C_CHILDREN, c_children);

@@ -19,7 +19,7 @@ d = agent(worlds, use_graph=False)          # warm-up move
 worlds, _ = worlds.step(d.actions)
 eng = engine_for(worlds, T)
 cp = net.packed()
-names = ['head', 'sample+advance', 'finish/fetch', 'visit: rest (child tops, state)', 'child terms', 'pass', 'newton/tail', 'visit: loads issued + parent scan', 'visit: cp.async wait', 'visit: adopt children', 'visit: lambda + scale row', '-']
+names = ['head', 'sample+advance', 'finish/fetch', 'gap after service', 'child terms', 'pass', 'newton/tail', 'visit: loads issued + parent scan', 'visit: cp.async wait', 'visit: adopt children', 'visit: lambda + scale row', '(lanes outside the visit)', 'visit: alpha seed, child tops']
 for label, prof_on in (('plain', False), ('clocked', True)):
     buf = torch.zeros(32, dtype=torch.int64, device='cuda')
     _lib.lib().bl_debug_set_phase_profile(_lib.ptr(buf) if prof_on else None)
@@ -37,7 +37,7 @@ for label, prof_on in (('plain', False), ('clocked', True)):
     if prof_on:
         c = buf.cpu().tolist()
         nw = max(c[15], 1)
-        tot = sum(c[:12])
+        tot = sum(c[:11]) + c[12]
         print(f'warps x launches = {nw}; avg cycles per warp per launch = {tot / nw:.0f}')
         for k, n in enumerate(names):
             print(f'  {n:16s} {c[k] / nw:9.0f} cycles  {100 * c[k] / tot:5.1f}%')
