@@ -47,6 +47,61 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0,
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- expand + env step (boardlaw/mcts/__init__.py:117-129), one lane per env ---------------------------------------------------
+// The lane moves its parent's board (BP bytes, 16-byte loads) into a lane-private shared-memory row `bdw`, places the stone /
+// relabels the group there (`stk`: flood-fill stack), and writes the row to the leaf's slot with 16-byte stores.
+__device__ __forceinline__ void bl_expand_one(const bl_tree &t, int sim, int b, int leaf, int parent, int action, uint32_t *bdw, uint8_t *stk) {
+    const int T = t.T, nq = t.BP >> 4;
+    const size_t node0 = (size_t)b * T;
+    if (action < 0) {
+        t.leaf[b] = -1;
+        atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_ERRORS), 1ull);
+        return;
+    }
+    uint8_t *bd = reinterpret_cast<uint8_t *>(bdw);
+    const uint4 *src = reinterpret_cast<const uint4 *>(t.board + (node0 + parent) * t.BP);
+    for (int i = 0; i < nq; i++) {
+        const uint4 v = src[i];
+        bdw[4 * i] = v.x; bdw[4 * i + 1] = v.y; bdw[4 * i + 2] = v.z; bdw[4 * i + 3] = v.w;
+    }
+    const bl_node pn = bl_ld_node(t.node + node0 + parent);
+    bl_node ln;
+    bool fresh = false;
+    if (leaf < 0) {                                             // new node in slot `sim`
+        leaf = sim;
+        fresh = true;
+        ln.parent = (int16_t)parent; ln.relation = (int16_t)action; ln.first_child = -1; ln.next_sib = pn.first_child;
+        ln.n = 0; ln.w[0] = 0; ln.w[1] = 0;
+        t.node[node0 + parent].first_child = (int16_t)sim;
+        t.parent_of[(size_t)b * ((T + 7) & ~7) + sim] = (int16_t)parent;
+        t.leaf[b] = (int16_t)leaf;
+    } else {                                                    // stopped at an existing terminal child: reuse its slot
+        ln = bl_ld_node(t.node + node0 + leaf);
+    }
+    const int seat = pn.seat;
+    const int win = bl_hex_place<uint8_t>(bd, stk, 1, t.S, seat, action);
+    const float r0 = win == 1 ? 1.f : (win == 2 ? -1.f : 0.f), r1 = win == 1 ? -1.f : (win == 2 ? 1.f : 0.f);   // +0, never -0
+    reinterpret_cast<uint32_t *>(t.aux + node0 + leaf)[0] = (uint32_t)bl_f2h(r0) | ((uint32_t)bl_f2h(r1) << 16);
+    ln.terminal = (uint8_t)win;                                 // 0, or the winner's code (1 = seat 0, 2 = seat 1): the backup
+    ln.seat = win ? 0 : (uint8_t)(1 - seat);                    // reads the rewards (+-1) off it
+    if (fresh) bl_st_node(t.node + node0 + leaf, ln);
+    else bl_st_node_stats(t.node + node0 + leaf, ln);
+    uint4 *dst = reinterpret_cast<uint4 *>(t.board + (node0 + leaf) * t.BP);
+    for (int i = 0; i < nq; i++)                                // a won game auto-resets to the empty board (hex/__init__.py:185-188)
+        dst[i] = win ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(bdw[4 * i], bdw[4 * i + 1], bdw[4 * i + 2], bdw[4 * i + 3]);
+}
+
+constexpr int XNT = 128;
+__global__ void __launch_bounds__(XNT) expand_step_kernel(bl_tree t, int sim) {
+    extern __shared__ __align__(16) uint8_t raw[];
+    const int tid = threadIdx.x, pw = (t.BP >> 2) | 1;            // row pitch in words (odd)
+    uint32_t *bdw = reinterpret_cast<uint32_t *>(raw) + (size_t)tid * pw;
+    uint8_t *stk = raw + (size_t)XNT * pw * 4 + (size_t)tid * pw * 4;
+    const int b = blockIdx.x * XNT + tid;
+    if (b >= t.B) return;
+    bl_expand_one(t, sim, b, t.leaf[b], t.leaf_parent[b], t.leaf_action[b], bdw, stk);
+}
+
 // service gate: the visit / sample / advance phases run when at least GATE_NUM/GATE_DEN of the warp's live lanes wait for them
 // (or nobody is in a pass); a lane therefore idles a trip or two now and then, and the warp does not pay the phases'
 // latency on every trip
@@ -58,7 +113,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 template <int NCH, bool PROF>
 __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_t seed,
                                                         ChildEntry *__restrict__ clists, int cap, unsigned long long *prof,
-                                                        int gate_num, int gate_den) {
+                                                        int gate_num, int gate_den, int fuse_expand) {
     constexpr int PS = 4 * NCH;                         // row pitch in floats; NCH odd => conflict-free 128-bit lane-private rows
     // the lane's third shared-memory row holds its child entries (16 B each; the rest go to global scratch) and, when it fits, a
     // copy of the env's parent row (scanned at every visit)
@@ -90,6 +145,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
     u64 tp[2 * NCH];                                  // lambda*pi of the current node, element pairs
     u64 cm[NW];                                       // bit a set: action a has a child
     int b = -1, cur = -1, parent = 0, action = -1, state = ST_DONE, nc = 0, it = 0, cur_seat = 0;
+    int res_leaf = -1, res_parent = 0, res_action = -1;       // this lane's finished descent (one env per lane when all are resident)
     float alpha = 1.f, error = 0.f, r = 0.f, c_puct = 0.f;
     uint32_t nzpos = 0;                               // first_nz | last_nz << 8 of the current row
     bool exhausted = false;                           // warp-uniform: the queue has nothing left
@@ -169,9 +225,10 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
             // ---- A: finished descents write their result and take the next env -------------------------------------------
             const bool fresh = state == ST_DONE;
             if (fresh && b >= 0) {
-                t.leaf[b] = (int16_t)cur;                          // existing terminal child, or -1: expand_step decides
+                t.leaf[b] = (int16_t)cur;                          // existing terminal child, or -1: the expand step decides
                 t.leaf_parent[b] = (int16_t)parent;
                 t.leaf_action[b] = (int16_t)action;
+                res_leaf = cur; res_parent = parent; res_action = action;
                 c_desc++;
             }
             const unsigned req = __ballot_sync(FULL, fresh);
@@ -406,6 +463,11 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
             }
         }
     }
+    // ---- expand + env step of the warp's 32 envs, fused when every env has its own lane (no separate launch) ---------------
+    if (fuse_expand) {
+        const int bm = (int)blockIdx.x * 32 + lane;
+        if (bm < t.B) bl_expand_one(t, sim, bm, res_leaf, res_parent, res_action, reinterpret_cast<uint32_t *>(ps), reinterpret_cast<uint8_t *>(pg));
+    }
     if (PROF) {
         tick(6);
 #pragma unroll
@@ -421,60 +483,6 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
     bl_count(t.counters, C_ITERS, c_iters);
     bl_count(t.counters, C_DESCENTS, c_desc);
 #undef tick
-}
-
-// ---- expand + env step (boardlaw/mcts/__init__.py:117-129), one lane per env ---------------------------------------------------
-// Each lane moves its parent's board (BP bytes, 16-byte loads) into a lane-private shared-memory row with an odd word pitch,
-// places the stone / relabels the group there, and writes the row to the leaf's slot with 16-byte stores.
-constexpr int XNT = 128;
-
-__global__ void __launch_bounds__(XNT) expand_step_kernel(bl_tree t, int sim) {
-    extern __shared__ __align__(16) uint8_t raw[];
-    const int tid = threadIdx.x;
-    const int T = t.T, nq = t.BP >> 4, pw = (t.BP >> 2) | 1;       // 16-byte pieces per board, row pitch in words (odd)
-    uint32_t *bdw = reinterpret_cast<uint32_t *>(raw) + (size_t)tid * pw;
-    uint8_t *bd = reinterpret_cast<uint8_t *>(bdw);
-    uint8_t *stk = raw + (size_t)XNT * pw * 4 + (size_t)tid * pw * 4;
-    const int b = blockIdx.x * XNT + tid;
-    if (b >= t.B) return;
-    const size_t node0 = (size_t)b * T;
-    int leaf = t.leaf[b];
-    const int parent = t.leaf_parent[b], action = t.leaf_action[b];
-    if (action < 0) {
-        t.leaf[b] = -1;
-        atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_ERRORS), 1ull);
-        return;
-    }
-    const uint4 *src = reinterpret_cast<const uint4 *>(t.board + (node0 + parent) * t.BP);
-    for (int i = 0; i < nq; i++) {
-        const uint4 v = src[i];
-        bdw[4 * i] = v.x; bdw[4 * i + 1] = v.y; bdw[4 * i + 2] = v.z; bdw[4 * i + 3] = v.w;
-    }
-    const bl_node pn = bl_ld_node(t.node + node0 + parent);
-    bl_node ln;
-    bool fresh = false;
-    if (leaf < 0) {                                             // new node in slot `sim`
-        leaf = sim;
-        fresh = true;
-        ln.parent = (int16_t)parent; ln.relation = (int16_t)action; ln.first_child = -1; ln.next_sib = pn.first_child;
-        ln.n = 0; ln.w[0] = 0; ln.w[1] = 0;
-        t.node[node0 + parent].first_child = (int16_t)sim;
-        t.parent_of[(size_t)b * ((T + 7) & ~7) + sim] = (int16_t)parent;
-        t.leaf[b] = (int16_t)leaf;
-    } else {                                                    // stopped at an existing terminal child: reuse its slot
-        ln = bl_ld_node(t.node + node0 + leaf);
-    }
-    const int seat = pn.seat;
-    const int win = bl_hex_place<uint8_t>(bd, stk, 1, t.S, seat, action);
-    const float r0 = win == 1 ? 1.f : (win == 2 ? -1.f : 0.f), r1 = win == 1 ? -1.f : (win == 2 ? 1.f : 0.f);   // +0, never -0
-    reinterpret_cast<uint32_t *>(t.aux + node0 + leaf)[0] = (uint32_t)bl_f2h(r0) | ((uint32_t)bl_f2h(r1) << 16);
-    ln.terminal = (uint8_t)win;                                 // 0, or the winner's code (1 = seat 0, 2 = seat 1): the backup
-    ln.seat = win ? 0 : (uint8_t)(1 - seat);                    // reads the rewards (+-1) off it
-    if (fresh) bl_st_node(t.node + node0 + leaf, ln);
-    else bl_st_node_stats(t.node + node0 + leaf, ln);
-    uint4 *dst = reinterpret_cast<uint4 *>(t.board + (node0 + leaf) * t.BP);
-    for (int i = 0; i < nq; i++)                                // a won game auto-resets to the empty board (hex/__init__.py:185-188)
-        dst[i] = win ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(bdw[4 * i], bdw[4 * i + 1], bdw[4 * i + 2], bdw[4 * i + 3]);
 }
 
 // ---- self test of the shared-reciprocal division -----------------------------------------------------------------------------
@@ -514,6 +522,7 @@ __global__ void __launch_bounds__(256) divtest_kernel(uint64_t seed, int n_div, 
 }
 
 unsigned long long *g_phase_prof = nullptr;
+bool g_last_fused = false;
 // service gate (see the kernel): BL_GATE="num/den" in the environment overrides the default for tuning runs
 int g_gate_num = BL_GATE_NUM, g_gate_den = BL_GATE_DEN;
 void read_gate_env() {
@@ -542,8 +551,11 @@ int launch_v3p(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, i
     const int need = (t->B + 31) / 32;
     const int grid = need < occ * BL_NUM_SMS ? need : occ * BL_NUM_SMS;
     if ((int64_t)grid * 32 * cap * (int64_t)sizeof(ChildEntry) > t->scratch_bytes) return -3;
+    // every env resident (one per lane) and the lane's rows big enough for a board + flood-fill stack: expand in the same kernel
+    const bool fused = (long long)grid * 32 >= t->B && t->BP <= 4 * 4 * NCH;
     descend_v3_kernel<NCH, PROF><<<grid, 32, smem, st>>>(*t, sim, rands, seed, reinterpret_cast<ChildEntry *>(t->scratch), cap, g_phase_prof,
-                                                         g_gate_num, g_gate_den);
+                                                         g_gate_num, g_gate_den, fused ? 1 : 0);
+    g_last_fused = fused;
     return (int)cudaGetLastError();
 }
 template <int NCH>
@@ -585,7 +597,7 @@ int bl_descend_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed
     else if (nch <= 43) rc = launch_v3<43>(t, sim, rands, seed, cap, st);
     else rc = -2;
     if (rc) return rc;
-    return bl_expand_step(t, sim, st);
+    return g_last_fused ? 0 : bl_expand_step(t, sim, st);
 }
 
 unsigned long long *bl_phase_prof() { return g_phase_prof; }
