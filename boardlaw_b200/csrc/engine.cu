@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256) set_eval_kernel(bl_tree t, int node, cons
                 hv[s] = HALF_IN ? reinterpret_cast<const bl_half *>(v_)[(size_t)b * 2 + s] : bl_f2h(reinterpret_cast<const float *>(v_)[(size_t)b * 2 + s]);
             uint32_t *ax = reinterpret_cast<uint32_t *>(t.aux + slot);
             ax[1] = (uint32_t)hv[0] | ((uint32_t)hv[1] << 16);
+            if (node < 0) reinterpret_cast<uint32_t *>(t.leaf_v)[b] = ax[1];
             // minnz_hi truncates the smallest nonzero pi downwards: the tiny-value test it feeds errs on the safe side
             reinterpret_cast<uint2 *>(ax)[1] = make_uint2(__float_as_uint(mx), (__float_as_uint(mn) >> 16) | ((uint32_t)(fz & 255) << 16) |
                                                                                   ((uint32_t)((lz < 0 ? 0 : lz) & 255) << 24));
@@ -211,10 +212,8 @@ __global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int si
         float val[2] = {0.f, 0.f};
         if (lane == 0) {
             leaf = t.leaf[b];
-            if (leaf >= 0) {
-                const bl_aux ax = bl_ld_aux(t.aux + (size_t)b * T + leaf);
-                val[0] = bl_h2f(ax.v[0]); val[1] = bl_h2f(ax.v[1]);
-            }
+            const uint32_t lv = reinterpret_cast<const uint32_t *>(t.leaf_v)[b];     // = aux[leaf].v, without the dependent load
+            if (leaf >= 0) { val[0] = bl_h2f((bl_half)(lv & 0xFFFF)); val[1] = bl_h2f((bl_half)(lv >> 16)); }
         }
         __syncwarp();
         if (lane == 0) {

@@ -32,11 +32,13 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int KC = 32;                     // K elements per weight stage
-constexpr int EPI_WARPS = 8;
-constexpr int WARP_LOAD = 8, WARP_MMA = 9;
-constexpr int TC_THREADS = 320;
+constexpr int L_WARPS = 8;                 // layer group: board staging, one-hot operand, layer epilogues
+constexpr int IO_WARPS = 4;                // heads group: softmax / tanh / tree write-back of the PREVIOUS tile, off the critical path
+constexpr int WARP_LOAD = 12, WARP_MMA = 13;
+constexpr int TC_THREADS = 448;
 constexpr int AH_COL = 256, AL_COL = 384;  // TMEM columns of the activation operand (hi, lo)
 constexpr int MAX_STAGES = 8;
+constexpr int HEADS_REG_COLS = 96;         // head columns an IO thread can hold in registers (Np <= 96: S <= 9)
 
 struct TcParams {
     const uint8_t *board;                  // env e's board at board + e*board_pitch (absolute frame, A bytes); tree mode: tree.board
@@ -111,6 +113,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -120,7 +128,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 warps of the layer group
 
 // UMMA shared-memory descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -138,52 +146,53 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return r;
 }
 
-struct Shape {              // derived sizes shared by the three roles and the host packer (networks.py mirrors them)
-    int NH, Wh, nk0, nk;    // N halves, columns per half, K chunks of layer 0 / of the residual layers and heads
-    int k0_split, k_split;  // chunks in the first K half (layer 0 / other layers)
+struct Shape {              // derived sizes shared by the roles and the host packer (networks.py mirrors them)
+    int nk0, nk;            // K chunks of layer 0 / of the residual layers and heads
     uint32_t stage_bytes;
 };
-__host__ __device__ inline Shape make_shape(int W, int K0p, int Np, int nsplit) {
+__host__ __device__ inline Shape make_shape(int W, int K0p, int Np) {
     Shape s;
-    s.NH = (nsplit == 2 && W >= 64) ? 2 : 1;
-    s.Wh = W / s.NH;
     s.nk0 = K0p / KC;
     s.nk = W / KC;
-    s.k0_split = s.NH == 2 ? (s.nk0 + 1) / 2 : s.nk0;
-    s.k_split = s.NH == 2 ? s.nk / 2 : s.nk;
-    const int rows = s.Wh > Np ? s.Wh : Np;
+    const int rows = W > Np ? W : Np;
     s.stage_bytes = (uint32_t)rows * KC * 2 * 2;
     return s;
 }
 __host__ __device__ inline int board_pitch_bytes(int A) { return 4 * (((A + 3) / 4) | 1); }   // odd number of words: conflict-free rows
-size_t smem_bytes(const Shape &s, int nstages, int A) {
-    return (size_t)s.stage_bytes * nstages + (size_t)TILE_M * board_pitch_bytes(A) + 1024 + 12 * TILE_M * sizeof(float);
-}
 size_t bias_bytes(int W, int D, int Np) { return ((size_t)(D + 1) * W + Np) * sizeof(float); }
+size_t smem_bytes(const Shape &s, int nstages, int A, int W, int D, int Np) {
+    return (size_t)s.stage_bytes * nstages + 2 * (size_t)TILE_M * board_pitch_bytes(A) + 1024 + 2 * TILE_M * sizeof(int32_t) + bias_bytes(W, D, Np);
+}
 
 #define TCK(k) do { if (p.prof) { const long long now_ = clock64(); pc[k] += now_ - tl; tl = now_; } } while (0)
 
 __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const Shape sh = make_shape(p.W, p.K0p, p.Np, p.nsplit);
+    const Shape sh = make_shape(p.W, p.K0p, p.Np);
     const int bpitch = board_pitch_bytes(p.A);                     // board tile row pitch
     uint8_t *stage0 = smem;
-    uint8_t *btile = stage0 + (size_t)sh.stage_bytes * p.nstages;  // [TILE_M][bpitch] boards of the tile
-    uint64_t *bars = reinterpret_cast<uint64_t *>(btile + (size_t)TILE_M * bpitch + ((16 - ((size_t)TILE_M * bpitch) % 16) % 16));
-    uint64_t *full = bars, *empty = bars + MAX_STAGES, *a_ready = bars + 2 * MAX_STAGES, *acc_full = a_ready + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 2);
-    int32_t *tseat = reinterpret_cast<int32_t *>(tmem_ptr + 4);   // [TILE_M] seat | node << 8 of the tile's rows
-    float *xch = reinterpret_cast<float *>(tseat + TILE_M);       // [12][TILE_M] partial results exchanged between the two warps of a quadrant
-    float *sbias = xch + 12 * TILE_M;                             // (D+1, W) cumulative biases, then the head bias (Np)
+    uint8_t *btile0 = stage0 + (size_t)sh.stage_bytes * p.nstages; // [2][TILE_M][bpitch] boards of two consecutive tiles
+    const size_t btile_bytes = (size_t)TILE_M * bpitch;            // multiple of 512
+    uint64_t *bars = reinterpret_cast<uint64_t *>(btile0 + 2 * btile_bytes);
+    uint64_t *full = bars, *empty = bars + MAX_STAGES, *a_ready = bars + 2 * MAX_STAGES, *acc_full = a_ready + 1, *oh_ready = a_ready + 2,
+             *heads_full = a_ready + 3, *board_free = a_ready + 4;   // board_free[2]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(a_ready + 6);
+    int32_t *tseat0 = reinterpret_cast<int32_t *>(tmem_ptr + 4);  // [2][TILE_M] seat | node << 8 of the tiles' rows
+    float *sbias = reinterpret_cast<float *>(tseat0 + 2 * TILE_M); // (D+1, W) cumulative biases, then the head bias (Np)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.W, D = p.D, A = p.A, S = p.S, Np = p.Np, K0p = p.K0p;
-    const int NH = sh.NH, Wh = sh.Wh;
     const int ntiles = (p.B + TILE_M - 1) / TILE_M;
+    const bool heads_in_regs = Np <= HEADS_REG_COLS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nstages; s++) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
-        for (int h = 0; h < 2; h++) { mbar_init(smem_u32(a_ready + h), EPI_WARPS); mbar_init(smem_u32(acc_full + h), 1); }
+        mbar_init(smem_u32(a_ready), L_WARPS);
+        mbar_init(smem_u32(acc_full), 1);
+        mbar_init(smem_u32(oh_ready), L_WARPS + IO_WARPS);
+        mbar_init(smem_u32(heads_full), 1);
+        mbar_init(smem_u32(board_free + 0), IO_WARPS);
+        mbar_init(smem_u32(board_free + 1), IO_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_ptr), 512);
@@ -192,17 +201,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
+    const float *bh = sbias + (size_t)(D + 1) * W;                 // head bias
 
     if (warp == WARP_LOAD) {
         // ---- weight loader: the blob is laid out in consumption order, one chunk per stage ----------------------------------
         if (lane == 0) {
             int stage = 0;
             uint32_t ph = 0;
-            const uint32_t body_bytes = (uint32_t)Wh * KC * 2 * 2, head_bytes = (uint32_t)Np * KC * 2 * 2;
+            const uint32_t body_bytes = (uint32_t)W * KC * 2 * 2, head_bytes = (uint32_t)Np * KC * 2 * 2;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t *src = p.blob;
                 for (int L = 0; L <= D + 1; L++) {
-                    const int nch = L == 0 ? sh.nk0 * NH : (L <= D ? sh.nk * NH : sh.nk);
+                    const int nch = L == 0 ? sh.nk0 : sh.nk;
                     const uint32_t cbytes = L <= D ? body_bytes : head_bytes;
                     for (int c = 0; c < nch; c++) {
                         mbar_wait(smem_u32(empty + stage), ph ^ 1);
@@ -218,11 +228,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
         // ---- MMA issuer ---------------------------------------------------------------------------------------------------------
         if (lane == 0) {
             int stage = 0;
-            uint32_t ph = 0, aph[2] = {0, 0};
+            uint32_t ph = 0, aph = 0, oph = 0;
             const bool lo_b = p.precision == 0;
             long long pc[3] = {0, 0, 0}, tl = p.prof ? clock64() : 0;       // [0] wait operand, [1] wait weights, [2] issue
-            // one K chunk (KC = 2 K-steps of 16) of one N block: D columns [dcol, dcol+N), A columns from acol
-            auto chunk = [&](uint32_t dcol, int N, int kchunk, bool lo_a, bool fresh_acc) {
+            // one K chunk (KC = 2 K-steps of 16): D columns [0, N), A columns from the chunk's K offset
+            auto chunk = [&](int N, int kchunk, bool lo_a, bool fresh_acc) {
                 TCK(2);
                 mbar_wait(smem_u32(full + stage), ph);
                 TCK(1);
@@ -233,52 +243,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                 for (int kk = 0; kk < KC / 16; kk++) {
                     const uint32_t acol = (uint32_t)(kchunk * KC + kk * 16) / 2, b_off = (uint32_t)kk * 2 * 128;
                     const uint64_t d_bhi = make_desc(sb + b_off, 128, (KC / 8) * 128);
-                    umma_ts(tmem + dcol, tmem + AH_COL + acol, d_bhi, idesc, !(fresh_acc && kk == 0));
-                    if (lo_b) umma_ts(tmem + dcol, tmem + AH_COL + acol, make_desc(sb + (uint32_t)N * KC * 2 + b_off, 128, (KC / 8) * 128), idesc, 1);
-                    if (lo_a) umma_ts(tmem + dcol, tmem + AL_COL + acol, d_bhi, idesc, 1);
+                    umma_ts(tmem, tmem + AH_COL + acol, d_bhi, idesc, !(fresh_acc && kk == 0));
+                    if (lo_b) umma_ts(tmem, tmem + AH_COL + acol, make_desc(sb + (uint32_t)N * KC * 2 + b_off, 128, (KC / 8) * 128), idesc, 1);
+                    if (lo_a) umma_ts(tmem, tmem + AL_COL + acol, d_bhi, idesc, 1);
                 }
                 umma_commit(smem_u32(empty + stage));              // frees the weight slot when these MMAs retire
                 if (++stage == p.nstages) { stage = 0; ph ^= 1; }
             };
-            auto wait_a = [&](int h) { TCK(2); mbar_wait(smem_u32(a_ready + h), aph[h]); TCK(0); aph[h] ^= 1; tc_fence_after(); };
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int L = 0; L <= D; L++) {
-                    const int nk = L == 0 ? sh.nk0 : sh.nk, ks = L == 0 ? sh.k0_split : sh.k_split;
+                    const int nk = L == 0 ? sh.nk0 : sh.nk;
                     const bool lo_a = L > 0 && p.precision == 0;
-                    // layer 0 overwrites z (first K chunk of each half), the residual layers accumulate onto it
-                    wait_a(0);
-                    for (int c = 0; c < ks; c++) chunk(0, Wh, c, lo_a, L == 0 && c == 0);                          // (h0, K0)
-                    if (NH == 2) {
-                        wait_a(1);
-                        for (int c = 0; c < ks; c++) chunk(Wh, Wh, c, lo_a, L == 0 && c == 0);                     // (h1, K0)
-                        for (int c = ks; c < nk; c++) chunk(0, Wh, c, lo_a, false);                               // (h0, K1)
-                    }
-                    umma_commit(smem_u32(acc_full + 0));
-                    if (NH == 2) {
-                        for (int c = ks; c < nk; c++) chunk(Wh, Wh, c, lo_a, false);                              // (h1, K1)
-                        umma_commit(smem_u32(acc_full + 1));
-                    }
+                    TCK(2);
+                    // layer 0: the one-hot operand is built AND the previous tile's head accumulator has left z
+                    if (L == 0) { mbar_wait(smem_u32(oh_ready), oph); oph ^= 1; }
+                    else { mbar_wait(smem_u32(a_ready), aph); aph ^= 1; }
+                    TCK(0);
+                    tc_fence_after();
+                    // layer 0 overwrites z (first K chunk), the residual layers accumulate onto it
+                    for (int c = 0; c < nk; c++) chunk(W, c, lo_a, L == 0 && c == 0);
+                    umma_commit(smem_u32(acc_full));
                 }
-                // heads: the accumulator re-uses z's columns [0, Np): wait until both halves of z have been consumed
-                wait_a(0);
-                if (NH == 2) wait_a(1);
-                for (int c = 0; c < sh.nk; c++) chunk(0, Np, c, p.precision == 0, c == 0);
-                umma_commit(smem_u32(acc_full + 0));
+                // heads: the accumulator re-uses z's columns [0, Np) once the last layer's epilogue has consumed z
+                TCK(2);
+                mbar_wait(smem_u32(a_ready), aph); aph ^= 1;
+                TCK(0);
+                tc_fence_after();
+                for (int c = 0; c < sh.nk; c++) chunk(Np, c, p.precision == 0, c == 0);
+                umma_commit(smem_u32(heads_full));
             }
             if (p.prof) { TCK(2); for (int k = 0; k < 3; k++) atomicAdd(p.prof + 16 + k, (unsigned long long)pc[k]); atomicAdd(p.prof + 31, 1ull); }
         }
-    } else {
-        // ---- epilogue warps -------------------------------------------------------------------------------------------------------
+    } else if (warp < L_WARPS) {
+        // ---- layer group -------------------------------------------------------------------------------------------------------------
         const int quad = warp & 3, hh = warp >> 2;
         const int row = quad * 32 + lane;
         const int et = threadIdx.x;                                // 0..255
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        uint32_t accph[2] = {0, 0};
-        long long pc[6] = {0, 0, 0, 0, 0, 0}, tl = p.prof ? clock64() : 0;   // [0] board staging [1] obs [2] wait acc [3] body epilogue [4] heads [5] wait heads
-        const int cph = Wh / 32;                                   // 32-column chunks per half
-        const int ch_begin = cph >= 2 ? hh * (cph / 2) : 0, ch_end = cph >= 2 ? ch_begin + cph / 2 : (hh == 0 ? cph : 0);
-        const uint8_t *brow = btile + (size_t)row * bpitch;
-        const float *bh = sbias + (size_t)(D + 1) * W;             // head bias
+        uint32_t accph = 0, hph = 0, bfph[2] = {0, 0};
+        long long pc[6] = {0, 0, 0, 0, 0, 0}, tl = p.prof ? clock64() : 0;   // [0] board staging [1] one-hot [2] wait acc [3] layer epilogue [5] wait heads of the previous tile
+        const int cpw = W / 32;                                    // 32-column chunks of a layer
+        const int ch_begin = cpw >= 2 ? hh * (cpw / 2) : 0, ch_end = cpw >= 2 ? ch_begin + cpw / 2 : (hh == 0 ? cpw : 0);
         // board staging: two threads per row, each moves half of the row's 4-byte words; the NEXT tile's words travel in
         // registers while the current tile is computed
         constexpr int MAXW = 22;                                   // words per thread: A <= 169 -> 43 words per row
@@ -319,10 +324,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
             }
         };
         fetch_tile(blockIdx.x);
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int m0 = tile * TILE_M;
-            // ---- the tile's boards (fetched during the previous tile) -> shared memory --------------------------------------------
-            epi_barrier();                                         // the previous tile's readers are done with btile
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const int buf = it & 1;
+            uint8_t *btile = btile0 + buf * btile_bytes;
+            int32_t *tseat = tseat0 + buf * TILE_M;
+            // ---- the tile's boards (fetched during the previous tile) -> shared memory; the heads group must be done with the
+            //      buffer's previous tenant (two tiles ago) ----------------------------------------------------------------------------
+            if (it >= 2) { mbar_wait(smem_u32(board_free + buf), bfph[buf]); bfph[buf] ^= 1; }
 #pragma unroll
             for (int k = 0; k < MAXW; k++)
                 if (k < wcount) *reinterpret_cast<uint32_t *>(btile + (size_t)srow * bpitch + (wfirst + k) * 4) = bw[k];
@@ -330,10 +339,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
             epi_barrier();
             fetch_tile(tile + gridDim.x);
             TCK(0);
-            const int m = m0 + row;
+            const int m = tile * TILE_M + row;
             const int32_t sv = tseat[row];
             const bool live = m < p.B && sv >= 0;
             const int seat = live ? (sv & 1) : 0;
+            const uint8_t *brow = btile + (size_t)row * bpitch;
+            // the operand columns are read by the previous tile's head MMAs: wait for them to retire
+            if (it >= 1) { mbar_wait(smem_u32(heads_full), hph); hph ^= 1; tc_fence_after(); }
+            TCK(5);
             // ---- observation operand (TensorIntake, heads.py:47-52): feature 2*cell + channel = one packed column per cell ---------
             {
                 // columns split between the two warps of the quadrant when both parts are whole 16-column stores
@@ -362,184 +375,209 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(smem_u32(a_ready + 0)); if (NH == 2) mbar_arrive(smem_u32(a_ready + 1)); }
+                if (lane == 0) mbar_arrive(smem_u32(oh_ready));
             }
             TCK(1);
             // ---- body layers: z -> next operand -------------------------------------------------------------------------------------
             for (int L = 0; L <= D; L++) {
                 const float *cb = sbias + (size_t)L * W;
                 const bool relu_out = L < D;
-                for (int h = 0; h < NH; h++) {
-                    // layer 0's one-hot operand lives in the very columns the next operand is written to, under a different
-                    // K <-> column mapping: nothing may be overwritten before ALL of layer 0's MMAs have retired
-                    if (L == 0 && NH == 2) {
-                        if (h == 0) { mbar_wait(smem_u32(acc_full + 0), accph[0]); mbar_wait(smem_u32(acc_full + 1), accph[1]); accph[0] ^= 1; accph[1] ^= 1; }
-                    } else {
-                        mbar_wait(smem_u32(acc_full + h), accph[h]);
-                        accph[h] ^= 1;
+                mbar_wait(smem_u32(acc_full), accph);
+                accph ^= 1;
+                tc_fence_after();
+                TCK(2);
+                uint32_t nxt[32];
+                if (ch_begin < ch_end) tmem_ld32(tmem + lane_base + ch_begin * 32, nxt);
+                for (int ch = ch_begin; ch < ch_end; ch++) {
+                    const int col = ch * 32;
+                    uint32_t acc[32];
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) acc[j] = nxt[j];
+                    if (ch + 1 < ch_end) tmem_ld32(tmem + lane_base + col + 32, nxt);      // in flight during this chunk's arithmetic
+                    uint32_t hi2[16], lo2[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 c4 = *reinterpret_cast<const float4 *>(cb + col + j);
+                        float a0 = __uint_as_float(acc[j]) + c4.x, a1 = __uint_as_float(acc[j + 1]) + c4.y;
+                        float a2 = __uint_as_float(acc[j + 2]) + c4.z, a3 = __uint_as_float(acc[j + 3]) + c4.w;
+                        if (relu_out) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                        const uint32_t h01 = pack_h2(a0, a1), h23 = pack_h2(a2, a3);
+                        const float2 f01 = __half22float2(*reinterpret_cast<const __half2 *>(&h01));
+                        const float2 f23 = __half22float2(*reinterpret_cast<const __half2 *>(&h23));
+                        hi2[j / 2] = h01; hi2[j / 2 + 1] = h23;
+                        lo2[j / 2] = pack_h2(a0 - f01.x, a1 - f01.y); lo2[j / 2 + 1] = pack_h2(a2 - f23.x, a3 - f23.y);
                     }
-                    tc_fence_after();
-                    TCK(2);
-                    uint32_t nxt[32];
-                    if (ch_begin < ch_end) tmem_ld32(tmem + lane_base + h * Wh + ch_begin * 32, nxt);
-                    for (int ch = ch_begin; ch < ch_end; ch++) {
-                        const int col = h * Wh + ch * 32;
-                        uint32_t acc[32];
+                    tmem_st16(tmem + lane_base + AH_COL + col / 2, hi2);
+                    if (p.precision == 0) tmem_st16(tmem + lane_base + AL_COL + col / 2, lo2);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(a_ready));
+                TCK(3);
+            }
+        }
+        if (p.prof && threadIdx.x == 0) for (int k = 0; k < 6; k++) atomicAdd(p.prof + 20 + k, (unsigned long long)pc[k]);
+    } else {
+        // ---- heads group: one warp per lane quadrant, one thread per env row; works on tile i while the other groups are already
+        //      on tile i+1 (the accumulator is pulled into registers first when it fits, which frees z for the next tile) -----------
+        const int quad = warp - L_WARPS;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        uint32_t hph = 0;
+        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = p.prof ? clock64() : 0;     // [0] wait heads [1] tail [2] acc->regs [3] mask [4] max [5] sum [6] write
+        const int nu = Np / 16;
+        // the first tile needs no hand-over of z
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(oh_ready));
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const int buf = it & 1;
+            const uint8_t *brow = btile0 + buf * btile_bytes + (size_t)row * bpitch;
+            const bool last = tile + (int)gridDim.x >= ntiles;
+            mbar_wait(smem_u32(heads_full), hph);
+            hph ^= 1;
+            tc_fence_after();
+            TCK(0);
+            const int m = tile * TILE_M + row;
+            const int32_t sv = tseat0[buf * TILE_M + row];
+            const bool live = m < p.B && sv >= 0;
+            const int seat = live ? (sv & 1) : 0;
+            float x[HEADS_REG_COLS];                               // raw head outputs of my row (fast path)
+            if (heads_in_regs) {
+#pragma unroll
+                for (int u = 0; u < HEADS_REG_COLS / 16; u++) {
+                    if (u < nu) {
+                        uint32_t acc[16];
+                        tmem_ld16(tmem + lane_base + u * 16, acc);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 32; j++) acc[j] = nxt[j];
-                        if (ch + 1 < ch_end) tmem_ld32(tmem + lane_base + col + 32, nxt);      // in flight during this chunk's arithmetic
-                        uint32_t hi2[16], lo2[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 c4 = *reinterpret_cast<const float4 *>(cb + col + j);
-                            float a0 = __uint_as_float(acc[j]) + c4.x, a1 = __uint_as_float(acc[j + 1]) + c4.y;
-                            float a2 = __uint_as_float(acc[j + 2]) + c4.z, a3 = __uint_as_float(acc[j + 3]) + c4.w;
-                            if (relu_out) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-                            const uint32_t h01 = pack_h2(a0, a1), h23 = pack_h2(a2, a3);
-                            const float2 f01 = __half22float2(*reinterpret_cast<const __half2 *>(&h01));
-                            const float2 f23 = __half22float2(*reinterpret_cast<const __half2 *>(&h23));
-                            hi2[j / 2] = h01; hi2[j / 2 + 1] = h23;
-                            lo2[j / 2] = pack_h2(a0 - f01.x, a1 - f01.y); lo2[j / 2 + 1] = pack_h2(a2 - f23.x, a3 - f23.y);
-                        }
-                        tmem_st16(tmem + lane_base + AH_COL + col / 2, hi2);
-                        if (p.precision == 0) tmem_st16(tmem + lane_base + AL_COL + col / 2, lo2);
+                        for (int j = 0; j < 16; j++) x[u * 16 + j] = __uint_as_float(acc[j]) + bh[u * 16 + j];
                     }
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(a_ready + h));
-                    TCK(3);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0 && !last) mbar_arrive(smem_u32(oh_ready));      // z is free: the next tile's layer 0 may overwrite it
+            }
+            TCK(2);
+            // legal moves (cell empty) of my row as a bitmask over head columns
+            unsigned long long vm[3] = {0, 0, 0};
+            {
+                int r = 0, c = 0;
+                for (int a = 0; a < A; a++) {
+                    const unsigned long long bit = brow[seat ? c * S + r : a] == BL_EMPTY ? 1ull : 0ull;
+                    vm[a >> 6] |= bit << (a & 63);
+                    if (++c == S) { c = 0; r++; }
                 }
             }
-            // ---- heads: masked log-softmax + tanh; the two warps of a quadrant share a row's columns in 16-column units ---------
-            mbar_wait(smem_u32(acc_full + 0), accph[0]);
-            accph[0] ^= 1;
-            tc_fence_after();
-            TCK(5);
-            {
-                const int nu = Np / 16, u_begin = hh ? nu / 2 : 0, u_end = hh ? nu : nu / 2;
-                // which of my columns are legal moves (cell empty), as a bitmask: bit (u - u_begin)*16 + j; at most 6 units per warp
-                unsigned long long vm0 = 0, vm1 = 0;
-                {
-                    int r = (u_begin * 16) / S, c = u_begin * 16 - r * S;
-                    const int ncols = (u_end - u_begin) * 16;
-                    for (int j = 0; j < ncols; j++) {
-                        const int a = u_begin * 16 + j;
-                        const unsigned long long bit = (a < A && brow[seat ? c * S + r : a] == BL_EMPTY) ? 1ull : 0ull;
-                        if (j < 64) vm0 |= bit << j; else vm1 |= bit << (j - 64);
-                        if (++c == S) { c = 0; r++; }
-                    }
-                }
-                auto ld16 = [&](int u, uint32_t (&acc)[16]) {
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                                 : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
-                                   "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]), "=r"(acc[15])
-                                 : "r"(tmem + lane_base + u * 16) : "memory");
+            auto vbits = [&](int u) { return (uint32_t)((vm[(u * 16) >> 6] >> ((u * 16) & 63)) & 0xFFFFull); };
+            auto unit = [&](int u, float (&y)[16]) {                // raw head outputs of columns [16u, 16u+16)
+                if (heads_in_regs) {
+#pragma unroll
+                    for (int uu = 0; uu < HEADS_REG_COLS / 16; uu++)
+                        if (uu == u) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) y[j] = x[uu * 16 + j];
+                        }
+                } else {
+                    uint32_t acc[16];
+                    tmem_ld16(tmem + lane_base + u * 16, acc);
                     tmem_wait_ld();
-                };
-                auto bits16 = [&](int u) { const int sft = (u - u_begin) * 16; return (uint32_t)((sft < 64 ? vm0 >> sft : vm1 >> (sft - 64)) & 0xFFFFull); };
-                // pass 1: raw logits of the valid actions -> max; the value head's column sits right after the policy's
-                float mx = -BL_INF_F, tanh_v = 0.f;
-                for (int u = u_begin; u < u_end; u++) {
-                    uint32_t acc[16];
-                    ld16(u, acc);
-                    const uint32_t vb = bits16(u);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const float x = __uint_as_float(acc[j]) + bh[u * 16 + j];
-                        if ((vb >> j) & 1u) mx = fmaxf(mx, x);
-                        if (u * 16 + j == A) tanh_v = tanhf(x);
-                    }
+                    for (int j = 0; j < 16; j++) y[j] = __uint_as_float(acc[j]) + bh[u * 16 + j];
                 }
-                xch[hh * TILE_M + row] = mx;
-                xch[(2 + hh) * TILE_M + row] = tanh_v;
-                epi_barrier();
-                mx = fmaxf(mx, xch[(hh ^ 1) * TILE_M + row]);
-                tanh_v += xch[(2 + (hh ^ 1)) * TILE_M + row];          // exactly one of the two warps saw column A
-                // pass 2: sum of exp
-                float sum = 0.f;
-                for (int u = u_begin; u < u_end; u++) {
-                    uint32_t acc[16];
-                    ld16(u, acc);
-                    const uint32_t vb = bits16(u);
+            };
+            TCK(3);
+            // pass 1: max over the legal actions; the value head's column sits right after the policy's
+            float mx = -BL_INF_F, tanh_v = 0.f;
+            for (int u = 0; u < nu; u++) {
+                float y[16];
+                unit(u, y);
+                const uint32_t vb = vbits(u);
 #pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if ((vb >> j) & 1u) sum += __expf((__uint_as_float(acc[j]) + bh[u * 16 + j]) - mx);
+                for (int j = 0; j < 16; j++) {
+                    if ((vb >> j) & 1u) mx = fmaxf(mx, y[j]);
+                    if (u * 16 + j == A) tanh_v = tanhf(y[j]);
                 }
-                xch[(4 + hh) * TILE_M + row] = sum;
-                epi_barrier();
-                sum += xch[(4 + (hh ^ 1)) * TILE_M + row];
-                const float lse = logf(sum);
-                // pass 3 — tree mode: logits -> half -> exp table -> pi row + row summary, straight into the search tree (what
-                // bl_tree_set_eval does for injected evaluations); otherwise fp32 logits / v for the caller
-                const int nd = sv >> 8;
-                const size_t slot = p.tree_mode && live ? (size_t)m * p.tree.T + nd : 0;
-                float pmax = 0.f, pmin = BL_INF_F;
-                int fz = 255, lz = -1;
-                for (int u = u_begin; u < u_end; u++) {
-                    uint32_t acc[16];
-                    ld16(u, acc);
-                    const uint32_t vb = bits16(u);
-                    if (live) {
-                        float lg[16];
+            }
+            TCK(4);
+            // pass 2: sum of exp
+            float sum = 0.f;
+            for (int u = 0; u < nu; u++) {
+                float y[16];
+                unit(u, y);
+                const uint32_t vb = vbits(u);
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if ((vb >> j) & 1u) sum += __expf(y[j] - mx);
+            }
+            const float lse = logf(sum);
+            TCK(5);
+            // pass 3 — tree mode: logits -> half -> exp table -> pi row + row summary, straight into the search tree (what
+            // bl_tree_set_eval does for injected evaluations); otherwise fp32 logits / v for the caller
+            const int nd = sv >> 8;
+            const size_t slot = p.tree_mode && live ? (size_t)m * p.tree.T + nd : 0;
+            float pmax = 0.f, pmin = BL_INF_F;
+            int fz = 255, lz = -1;
+            for (int u = 0; u < nu; u++) {
+                float y[16];
+                unit(u, y);
+                const uint32_t vb = vbits(u);
+                if (live) {
+                    float lg[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) lg[j] = ((vb >> j) & 1u) ? (y[j] - mx) - lse : -BL_INF_F;
+                    if (p.tree_mode) {
+                        float pv[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {             // 16 independent table look-ups in flight
+                            const int a = u * 16 + j;
+                            const bl_half hl = bl_f2h(lg[j]);
+                            pv[j] = ((vb >> j) & 1u) ? p.tree.exp_lut[hl] : 0.f;     // exp(-inf) = 0 for illegal / padding columns
+                            if (a < A && p.tree.logits) p.tree.logits[slot * A + a] = hl;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int a = u * 16 + j;
+                            if (pv[j] != 0.f) { pmax = fmaxf(pmax, pv[j]); pmin = fminf(pmin, pv[j]); fz = min(fz, a); lz = max(lz, a); }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            if (u * 16 + j < p.tree.AP)
+                                *reinterpret_cast<float4 *>(p.tree.pi + slot * p.tree.AP + u * 16 + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 16; j++)
-                            lg[j] = ((vb >> j) & 1u) ? ((__uint_as_float(acc[j]) + bh[u * 16 + j]) - mx) - lse : -BL_INF_F;
-                        if (p.tree_mode) {
-                            float pv[16];
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {             // 16 independent table look-ups in flight
-                                const int a = u * 16 + j;
-                                const bl_half hl = bl_f2h(lg[j]);
-                                pv[j] = ((vb >> j) & 1u) ? p.tree.exp_lut[hl] : 0.f;     // exp(-inf) = 0 for illegal / padding columns
-                                if (a < A && p.tree.logits) p.tree.logits[slot * A + a] = hl;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                const int a = u * 16 + j;
-                                if (pv[j] != 0.f) { pmax = fmaxf(pmax, pv[j]); pmin = fminf(pmin, pv[j]); fz = min(fz, a); lz = max(lz, a); }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4)
-                                if (u * 16 + j < p.tree.AP)
-                                    *reinterpret_cast<float4 *>(p.tree.pi + slot * p.tree.AP + u * 16 + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; j++)
-                                if (u * 16 + j < A) p.logits[(size_t)m * A + u * 16 + j] = lg[j];
-                        }
+                            if (u * 16 + j < A) p.logits[(size_t)m * A + u * 16 + j] = lg[j];
                     }
                 }
+            }
+            if (live) {
+                const float v0 = seat ? -tanh_v : tanh_v, v1 = -v0;
                 if (p.tree_mode) {
-                    // row summary: combine the two warps' partial (max, min, first, last)
-                    xch[(6 + hh) * TILE_M + row] = pmax;
-                    xch[(8 + hh) * TILE_M + row] = pmin;
-                    xch[(10 + hh) * TILE_M + row] = __int_as_float(fz | (lz < 0 ? 0xFFFF00 : lz << 8));
-                    epi_barrier();
-                    if (hh == 0 && live) {
-                        pmax = fmaxf(pmax, xch[7 * TILE_M + row]);
-                        pmin = fminf(pmin, xch[9 * TILE_M + row]);
-                        const int o = __float_as_int(xch[11 * TILE_M + row]);
-                        fz = min(fz, o & 255);
-                        const int olz = (o >> 8) == 0xFFFF ? -1 : (o >> 8);
-                        lz = max(lz, olz);
-                        const float v0 = seat ? -tanh_v : tanh_v, v1 = -v0;
-                        uint32_t *ax = reinterpret_cast<uint32_t *>(p.tree.aux + slot);
-                        ax[1] = (uint32_t)bl_f2h(v0) | ((uint32_t)bl_f2h(v1) << 16);
-                        reinterpret_cast<uint2 *>(ax)[1] = make_uint2(__float_as_uint(pmax), (__float_as_uint(pmin) >> 16) | ((uint32_t)(fz & 255) << 16) |
-                                                                                                   ((uint32_t)((lz < 0 ? 0 : lz) & 255) << 24));
-                    }
-                } else if (hh == 0 && live) {
-                    const float v0 = seat ? -tanh_v : tanh_v;
+                    uint32_t *ax = reinterpret_cast<uint32_t *>(p.tree.aux + slot);
+                    ax[1] = (uint32_t)bl_f2h(v0) | ((uint32_t)bl_f2h(v1) << 16);
+                    reinterpret_cast<uint32_t *>(p.tree.leaf_v)[m] = ax[1];
+                    reinterpret_cast<uint2 *>(ax)[1] = make_uint2(__float_as_uint(pmax), (__float_as_uint(pmin) >> 16) | ((uint32_t)(fz & 255) << 16) |
+                                                                                               ((uint32_t)((lz < 0 ? 0 : lz) & 255) << 24));
+                } else {
                     p.v[(size_t)m * 2] = v0;
-                    p.v[(size_t)m * 2 + 1] = -v0;
+                    p.v[(size_t)m * 2 + 1] = v1;
                 }
             }
             tc_fence_before();
-            TCK(4);
+            __syncwarp();
+            if (lane == 0) {
+                if (!heads_in_regs && !last) mbar_arrive(smem_u32(oh_ready));  // slow path: z was needed until now
+                mbar_arrive(smem_u32(board_free + buf));
+            }
+            TCK(6);
         }
-        if (p.prof && threadIdx.x == 0) for (int k = 0; k < 6; k++) atomicAdd(p.prof + 20 + k, (unsigned long long)pc[k]);
+        if (p.prof && lane == 0 && quad == 0) {
+            atomicAdd(p.prof + 25, (unsigned long long)pc[0]);
+            for (int k = 2; k < 7; k++) atomicAdd(p.prof + 24 + k, (unsigned long long)pc[k]);     // slots 26..30
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -554,14 +592,13 @@ int launch(const bl_fc_params *p, TcParams &k, int B, cudaStream_t st) {
     k.B = B; k.S = S; k.A = A; k.W = W; k.D = p->D; k.precision = p->precision;
     k.K0p = (2 * A + KC - 1) / KC * KC;
     k.Np = (A + 1 + 31) / 32 * 32;
-    k.nsplit = p->tc_nsplit == 2 ? 2 : 1;
-    const Shape sh = make_shape(W, k.K0p, k.Np, k.nsplit);
+    k.nsplit = 1;
+    const Shape sh = make_shape(W, k.K0p, k.Np);
     int ns = MAX_STAGES;
-    const size_t extra = bias_bytes(W, p->D, k.Np);
-    while (ns >= 2 && smem_bytes(sh, ns, A) + extra > 227 * 1024) ns--;
+    while (ns >= 2 && smem_bytes(sh, ns, A, W, p->D, k.Np) > 227 * 1024) ns--;
     if (ns < 2) return -2;
     k.nstages = ns;
-    const size_t smem = smem_bytes(sh, ns, A) + extra;
+    const size_t smem = smem_bytes(sh, ns, A, W, p->D, k.Np);
     cudaError_t e = cudaFuncSetAttribute(fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int ntiles = (B + TILE_M - 1) / TILE_M;

@@ -60,7 +60,7 @@ class FCModel(nn.Module):
         self.tensor_cores = True
         # tile order of the packed operands (bl_fc_params.tc_nsplit); BL_TC_NSPLIT overrides for experiments
         import os
-        self.tc_nsplit = int(os.environ.get('BL_TC_NSPLIT', '1'))
+        self.tc_nsplit = 1      # whole-N tiles: one tcgen05.mma issue costs ~120 cycles, so N = W/2 tiles are issue-bound
 
     def sampler(self, logits, test=False):
         if test:

@@ -190,6 +190,8 @@ typedef struct bl_tree {
     int16_t *leaf;        /* (B,)   i16 leaf of the current simulation                              */
     int16_t *leaf_parent; /* (B,)   i16                                                             */
     int16_t *leaf_action; /* (B,)   i16                                                             */
+    bl_half *leaf_v;      /* (B,Sn) half: the value just evaluated at each env's leaf (copy of aux[leaf].v, so the backup does not
+                             chase leaf -> aux)                                                                       */
     bl_half *prior;       /* (B,A)  half: the (noised) root logits as stored, = decisions.logits[:,0]       */
     float *qrange;        /* (T+1,2) per-simulation (min,max) of w/(n+1e-4), ordered-int encoded    */
     uint64_t *counters;   /* (8,) policy evals, children seen, newton iters, descents, backup nodes, errors, move, queue */

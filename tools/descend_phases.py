@@ -44,6 +44,7 @@ for label, prof_on in (('plain', False), ('clocked', True)):
         ncta = max(c[31], 1)
         print(f'network kernel: CTAs x launches = {ncta}')
         for k, n in ((16, 'mma: wait operand'), (17, 'mma: wait weights'), (18, 'mma: issue'), (20, 'epi: board staging'), (21, 'epi: one-hot operand'),
-                     (22, 'epi: wait accumulator'), (23, 'epi: layer epilogue'), (24, 'epi: heads'), (25, 'epi: wait heads')):
+                     (22, 'epi: wait accumulator'), (23, 'epi: layer epilogue'), (25, 'heads: wait accumulator'), (26, 'heads: acc -> registers'),
+                     (27, 'heads: legal-move mask'), (28, 'heads: max'), (29, 'heads: sum exp'), (30, 'heads: logits/pi/stores')):
             print(f'  {n:24s} {c[k] / ncta:9.0f} cycles per CTA per launch')
 _lib.lib().bl_debug_set_phase_profile(None)
