@@ -28,6 +28,7 @@ SOURCES = {
     'descend.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
     'net.cu': [],
     'net_tc.cu': [],
+    'net_tc_wide.cu': [],
     'host.cu': [],
 }
 

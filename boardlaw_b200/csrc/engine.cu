@@ -340,6 +340,9 @@ __global__ void __launch_bounds__(256) gather_leaves_kernel(bl_tree t, int node,
 // net_tc.cu
 int bl_fc_forward_tc_tree(const bl_fc_params *p, const bl_tree *t, cudaStream_t st);
 bool bl_fc_tc_supported(const bl_fc_params *p);
+// net_tc_wide.cu
+int bl_fc_forward_wide_tree(const bl_fc_params *p, const bl_tree *t, void *scratch, cudaStream_t st);
+bool bl_fc_wide_supported(const bl_fc_params *p);
 namespace {
 
 int grid1d(long long n, int block) {
@@ -444,6 +447,7 @@ extern "C" int bl_tree_eval_leaves(const bl_tree *t, const bl_fc_params *p, int 
     // tensor-core path: one kernel reads the leaf boards from the tree and writes pi rows / summaries / values back into it
     if (bl_fc_tc_supported(p)) return bl_fc_forward_tc_tree(p, t, bl_cu(stream));
     EvalScratch s = split_scratch(t, scratch);
+    if (bl_fc_wide_supported(p)) return bl_fc_forward_wide_tree(p, t, s.net, bl_cu(stream));
     gather_leaves_kernel<<<grid1d((long long)t->B * t->A, 256), 256, 0, bl_cu(stream)>>>(*t, -1, s.board, s.seats);
     int e = bl_fc_forward(p, s.board, s.seats, s.logits, s.v, s.net, t->B, stream);
     if (e) return e;

@@ -140,10 +140,17 @@ __global__ void __launch_bounds__(256) heads_kernel(
 int bl_fc_forward_tc(const bl_fc_params *p, const uint8_t *board, long long board_pitch, const int32_t *seats, float *logits,
                      float *v, int B, cudaStream_t st);
 bool bl_fc_tc_supported(const bl_fc_params *p);
+// net_tc_wide.cu
+int bl_fc_forward_wide(const bl_fc_params *p, const uint8_t *board, long long board_pitch, const int32_t *seats, float *logits,
+                       float *v, void *scratch, int B, cudaStream_t st);
+bool bl_fc_wide_supported(const bl_fc_params *p);
+int64_t bl_fc_wide_scratch_bytes(const bl_fc_params *p, int B);
 
-extern "C" int bl_fc_uses_tensor_cores(const bl_fc_params *p) { return bl_fc_tc_supported(p) ? 1 : 0; }
+extern "C" int bl_fc_uses_tensor_cores(const bl_fc_params *p) { return (bl_fc_tc_supported(p) || bl_fc_wide_supported(p)) ? 1 : 0; }
 
 extern "C" int64_t bl_fc_scratch_bytes(const bl_fc_params *p, int B) {
+    if (bl_fc_tc_supported(p)) return 0;
+    if (bl_fc_wide_supported(p)) return bl_fc_wide_scratch_bytes(p, B);
     return (int64_t)sizeof(float) * B * (2 * (int64_t)p->W + (int64_t)p->S * p->S);
 }
 
@@ -155,6 +162,7 @@ extern "C" int bl_fc_forward(const bl_fc_params *p, const uint8_t *board, const 
     cudaStream_t st = bl_cu(stream);
     const int S = p->S, A = S * S, W = p->W;
     if (bl_fc_tc_supported(p)) return bl_fc_forward_tc(p, board, (long long)A, seats, logits, v, B, st);
+    if (bl_fc_wide_supported(p)) return bl_fc_forward_wide(p, board, (long long)A, seats, logits, v, scratch_, B, st);
     float *x0 = scratch, *x1 = scratch + (size_t)B * W, *raw = scratch + (size_t)2 * B * W;
     dim3 grid((B + TM - 1) / TM, (W + TN - 1) / TN);
     fc_layer_kernel<true, false, false><<<grid, NTHREADS, 0, st>>>(nullptr, board, seats, S, p->w_in, p->b_in, nullptr,

@@ -85,8 +85,9 @@ class FCModel(nn.Module):
                 w_pol=f(self.policy.core.weight), b_pol=f(self.policy.core.bias),
                 w_val=f(self.value.core.weight).reshape(-1), b_val=f(self.value.core.bias).reshape(-1))
             tc = {}
-            if self.tensor_cores and W in (32, 64, 128, 256) and self.boardsize ** 2 + 1 <= 256:
-                blob, b_head = pack_tensor_core_operands(pack, self.boardsize, self.tc_nsplit)
+            if self.tensor_cores and W in (32, 64, 128, 256, 512) and self.boardsize ** 2 + 1 <= 256:
+                # W = 512 runs net_tc_wide.cu: 16-wide K chunks, whole-N tiles
+                blob, b_head = pack_tensor_core_operands(pack, self.boardsize, self.tc_nsplit, kc=16 if W == 512 else KC, wide=W == 512)
                 pack['packed'], pack['b_head'] = blob, b_head
                 tc = dict(packed=blob.data_ptr(), b_head=b_head.data_ptr(), tc_nsplit=self.tc_nsplit)
             cp = _lib.FCParams(
@@ -123,7 +124,7 @@ class FCModel(nn.Module):
 KC = 32     # K elements per operand tile (net_tc.cu)
 
 
-def _split_tiles(w, n_pad, k_pad):
+def _split_tiles(w, n_pad, k_pad, KC=KC):
     """(N,K) fp32 -> (k_pad/KC, 2, n_pad/8, KC/8, 8, 8) fp16: per K-chunk a hi block then a lo block, each in the UMMA
     canonical K-major no-swizzle layout: element (n, k) at ((n/8)*(KC/8) + k/8)*64 + (n%8)*8 + k%8 halves."""
     N, K = w.shape
@@ -136,23 +137,27 @@ def _split_tiles(w, n_pad, k_pad):
     return t.permute(3, 0, 1, 4, 2, 5).contiguous()                      # (chunk, 2, n/8, k/8, n%8, k%8)
 
 
-def pack_tensor_core_operands(pack, boardsize, nsplit=1):
+def pack_tensor_core_operands(pack, boardsize, nsplit=1, kc=KC, wide=False):
     """The weight blob fc_tc_kernel streams, in the kernel's consumption order (net_tc.cu): per layer the four blocks
     (N half 0, K half 0), (N half 1, K half 0), (N half 0, K half 1), (N half 1, K half 1) — one block when W < 64 — then the
     fused head [policy ; value]; every weight split as hi = fp16(w), lo = fp16(w - hi).  The ReZero gate is folded into the
     residual weights (alpha_k W_k), and the biases are returned as the cumulative vectors c_0 = b_in, c_k = c_{k-1} +
-    alpha_k b_k the kernel adds on the way out of the accumulator, followed by the head bias."""
+    alpha_k b_k the kernel adds on the way out of the accumulator, followed by the head bias.
+    ``wide`` (net_tc_wide.cu, W = 512): 16-wide K chunks, and per layer all the chunks of N half 0 (rows 0..255), then all of half 1."""
     A = boardsize * boardsize
     W = pack['w_in'].shape[0]
-    k0p = (2 * A + KC - 1) // KC * KC
+    k0p = (2 * A + kc - 1) // kc * kc
     n_p = (A + 1 + 31) // 32 * 32
     nh = 2 if (nsplit == 2 and W >= 64) else 1
     wh = W // nh
+    _split = lambda w, n_pad, k_pad: _split_tiles(w, n_pad, k_pad, kc)
 
     def body(w, k_pad):
-        nk = k_pad // KC
+        if wide:
+            return [_split(w[h * 256:(h + 1) * 256], 256, k_pad).reshape(-1) for h in range(W // 256)]
+        nk = k_pad // kc
         ks = ((nk + 1) // 2 if k_pad == k0p and w is pack['w_in'] else nk // 2) if nh == 2 else nk
-        tiles = [_split_tiles(w[h * wh:(h + 1) * wh], wh, k_pad) for h in range(nh)]      # (nk, 2, wh/8, KC/8, 8, 8) each
+        tiles = [_split(w[h * wh:(h + 1) * wh], wh, k_pad) for h in range(nh)]      # (nk, 2, wh/8, KC/8, 8, 8) each
         if nh == 1:
             return [tiles[0].reshape(-1)]
         return [tiles[0][:ks].reshape(-1), tiles[1][:ks].reshape(-1), tiles[0][ks:].reshape(-1), tiles[1][ks:].reshape(-1)]
@@ -164,7 +169,7 @@ def pack_tensor_core_operands(pack, boardsize, nsplit=1):
         parts += body(alpha * pack['w_res'][k], W)
         cb.append(cb[-1] + alpha * pack['b_res'][k])
     head = torch.cat([pack['w_pol'], pack['w_val'][None]], 0)            # (A+1, W)
-    parts.append(_split_tiles(head, n_p, W).reshape(-1))
+    parts.append(_split(head, n_p, W).reshape(-1))
     b_head = pack['b_pol'].new_zeros((n_p,))
     b_head[:A] = pack['b_pol']
     b_head[A] = pack['b_val'][0]

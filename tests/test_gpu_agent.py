@@ -46,14 +46,15 @@ def test_agent_surface():
     assert torch.equal(d.actions, d.logits.argmax(-1))
 
 
-def test_fused_vs_op_level_same_device():
+@pytest.mark.parametrize('S,W,D,B,T', [(7, 64, 3, 300, 32), (11, 512, 2, 300, 24)])
+def test_fused_vs_op_level_same_device(S, W, D, B, T):
     """The fused engine and the op-level ``MCTS`` loop, both on the GPU with the same network kernels and injected
-    randomness, build the same search (they share no tree code above mcts_core.cuh)."""
+    randomness, build the same search (they share no tree code above mcts_core.cuh).  W = 512 covers the wide network
+    kernel's tree mode (net_tc_wide.cu) against its plain mode."""
     from boardlaw_b200.engine import SearchEngine
     from boardlaw_b200.hex import Hex
     from boardlaw_b200.mcts import MCTS
-    S, B, T = 7, 300, 32
-    agent, sd = make_agent(S, 64, 3, T, seed=3)
+    agent, sd = make_agent(S, W, D, T, seed=3)
     net = agent.network
     w0 = gu.start_position(S, B, 10, seed=1)
     world = Hex(board=w0.board.cuda(), seats=w0.seats.cuda())

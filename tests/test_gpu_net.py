@@ -45,10 +45,12 @@ def test_forward_golden(S, W, D):
 
 @pytest.mark.parametrize('tensor_cores', [True, False])
 @pytest.mark.parametrize('S,W,D,B', [(9, 256, 4, 4096), (7, 128, 4, 1000), (13, 64, 2, 517), (3, 2, 4, 64), (11, 512, 8, 512),
-                                     (5, 32, 2, 300), (9, 256, 0, 129), (9, 64, 1, 40000)])
+                                     (5, 32, 2, 300), (9, 256, 0, 129), (9, 64, 1, 40000),
+                                     (11, 512, 8, 20000), (13, 512, 2, 300), (5, 512, 1, 129), (9, 512, 0, 200)])
 def test_forward_vs_oracle(S, W, D, B, tensor_cores):
-    """tensor_cores=True: tcgen05 split-fp16 kernel where the shape fits (W in 32/64/128/256), CUDA-core fp32 kernels
-    otherwise; False forces the CUDA-core path.  Both within 1e-5 of the fp32 CPU reference."""
+    """tensor_cores=True: tcgen05 split-fp16 kernels where the shape fits (W in 32/64/128/256: net_tc.cu; W = 512:
+    net_tc_wide.cu), CUDA-core fp32 kernels otherwise; False forces the CUDA-core path.  Both within 1e-5 of the fp32 CPU
+    reference."""
     from oracle import pyref
     sd = pyref.synth_state_dict(S, W, D, seed=S + W)
     w = gu.start_position(S, B, S * S // 2, seed=W)
