@@ -37,6 +37,8 @@ constexpr int WARP_LOADW = 12, WARP_LOADA = 13, WARP_MMA = 14;
 constexpr int THREADS = 480;
 constexpr int MAX_STAGES = 8;
 constexpr int LO_COL = 256;                // TMEM columns of the cross-term accumulator
+constexpr int CL = 2;                      // CTAs per cluster: they work on different tiles in lockstep and share every weight chunk —
+                                           // each loads 1/CL of it and multicasts it to all (the kernel is L2-bandwidth-bound)
 constexpr uint32_t ACT_BLOCK = TILE_M * KC * 2;    // one hi (or lo) operand block of a chunk: 128 rows x 16 K halves
 constexpr uint32_t ACT_CHUNK = 2 * ACT_BLOCK;      // hi block, lo block
 constexpr uint32_t LBO = 128, SBO = (KC / 8) * 128;   // canonical K-major no-swizzle: K-adjacent / row-group-adjacent core matrices
@@ -65,7 +67,7 @@ size_t smem_bytes(int nstages, int A, int W, int D, int Np) {
 
 #define TCK(k) do { if (p.prof) { const long long now_ = clock64(); pc[k] += now_ - tl; tl = now_; } } while (0)
 
-__global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_constant__ WideParams p) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_constant__ WideParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int W = p.W, D = p.D, A = p.A, S = p.S, Np = p.Np, K0p = p.K0p;
     const uint32_t wstage_bytes = (uint32_t)NI * KC * 4;             // one N half of a K chunk: hi block, lo block
@@ -85,13 +87,17 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (p.B + TILE_M - 1) / TILE_M;
     const int nk0 = K0p / KC, nk = W / KC;
+    // the cluster's CTAs run the same number of tiles (tile0 is cluster-uniform; a CTA whose tile is past the end works on dead rows)
+    uint32_t crank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int tile_first = (int)blockIdx.x - (int)crank;
     const size_t strip = strip_bytes(W, K0p);
     uint8_t *scr = p.scratch + (size_t)blockIdx.x * 2 * strip;      // operand strips: layer L reads strip L & 1
-    float *zscr = reinterpret_cast<float *>(p.scratch + (size_t)gridDim.x * 2 * strip + (size_t)blockIdx.x * TILE_M * W * 4);   // [W/32][TILE_M][32]
+    float *zscr = reinterpret_cast<float *>(p.scratch + (size_t)gridDim.x * 2 * strip + (size_t)blockIdx.x * TILE_M * W * 4);   // [W/16][4][TILE_M] x 16 bytes
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nstages; s++) {
-            mbar_init(smem_u32(full_w + s), 1); mbar_init(smem_u32(full_a + s), 1); mbar_init(smem_u32(empty + s), 1);
+            mbar_init(smem_u32(full_w + s), 1); mbar_init(smem_u32(full_a + s), 1); mbar_init(smem_u32(empty + s), CL);   // every CTA's MMAs free a slot
         }
         mbar_init(smem_u32(a_ready), L_WARPS);
         mbar_init(smem_u32(acc_full), 1);
@@ -106,6 +112,7 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
     for (int i = threadIdx.x; i < (D + 1) * W + Np; i += THREADS) sbias[i] = p.cbias[i];
     tc_fence_before();
     __syncthreads();
+    cluster_sync();                                                // the peers' barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     const float *bh = sbias + (size_t)(D + 1) * W;                 // head bias
@@ -116,15 +123,17 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
             int stage = 0;
             uint32_t ph = 0;
             const uint32_t body_bytes = wstage_bytes, head_bytes = (uint32_t)Np * KC * 4;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile0 = tile_first; tile0 < ntiles; tile0 += gridDim.x) {
                 const uint8_t *src = p.blob;
                 for (int L = 0; L <= D + 1; L++) {
                     const int nch = (L == 0 ? nk0 : nk) * (L <= D ? W / NI : 1);     // the body layers: N half 0's chunks, then half 1's
                     const uint32_t cbytes = L <= D ? body_bytes : head_bytes;
                     for (int c = 0; c < nch; c++) {
-                        mbar_wait(smem_u32(empty + stage), ph ^ 1);
-                        mbar_expect_tx(smem_u32(full_w + stage), cbytes);
-                        bulk_g2s(smem_u32(wstage0 + (size_t)wstage_bytes * stage), src, cbytes, smem_u32(full_w + stage));
+                        mbar_wait(smem_u32(empty + stage), ph ^ 1);       // freed by every CTA of the cluster
+                        mbar_expect_tx(smem_u32(full_w + stage), cbytes);   // my share + the peers', all landing in my slot
+                        const uint32_t share = cbytes / CL;
+                        bulk_g2s_multicast(smem_u32(wstage0 + (size_t)wstage_bytes * stage) + crank * share, src + crank * share, share,
+                                           smem_u32(full_w + stage), (uint16_t)((1u << CL) - 1));
                         src += cbytes;
                         if (++stage == p.nstages) { stage = 0; ph ^= 1; }
                     }
@@ -136,15 +145,17 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t ph = 0, aph = 0, oph = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile0 = tile_first; tile0 < ntiles; tile0 += gridDim.x) {
                 for (int L = 0; L <= D + 1; L++) {
                     const int nch = L == 0 ? nk0 : nk;
                     // layer 0: the one-hot operand is written AND the previous tile's head accumulator has left z
                     if (L == 0) { mbar_wait(smem_u32(oh_ready), oph); oph ^= 1; }
-                    else { mbar_wait(smem_u32(a_ready), aph); aph ^= 1; }
                     const uint8_t *src = scr + (size_t)(L & 1) * strip;
                     for (int h = 0; h < (L <= D ? W / NI : 1); h++)       // every N half streams the whole operand again
                         for (int c = 0; c < nch; c++) {
+                            // the producing layer publishes its operand half by half (a_ready after each half's epilogue): the first
+                            // K half can be in the ring while the second is still being written
+                            if (L > 0 && h == 0 && c % (nk / (W / NI)) == 0) { mbar_wait(smem_u32(a_ready), aph); aph ^= 1; }
                             mbar_wait(smem_u32(empty + stage), ph ^ 1);
                             mbar_expect_tx(smem_u32(full_a + stage), ACT_CHUNK);
                             bulk_g2s(smem_u32(astage0 + (size_t)ACT_CHUNK * stage), src + (size_t)c * ACT_CHUNK, ACT_CHUNK, smem_u32(full_a + stage));
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
             uint32_t ph = 0, fph = 0;
             const bool lo_b = p.precision == 0;
             long long pc[3] = {0, 0, 0}, tl = p.prof ? clock64() : 0;       // [0] wait operand / accumulator hand-over, [1] wait weights, [2] issue
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile0 = tile_first; tile0 < ntiles; tile0 += gridDim.x) {
                 for (int L = 0; L <= D + 1; L++) {
                     const bool heads = L == D + 1;
                     const int nch = L == 0 ? nk0 : nk;
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
                             umma_ss(tmem, a_hi, b_hi, idesc, c > 0);
                             if (lo_b) umma_ss(tmem + LO_COL, a_hi, make_desc(wb + (uint32_t)ninst * KC * 2, LBO, SBO), idesc, c > 0);
                             if (lo_a) umma_ss(tmem + LO_COL, make_desc(ab + ACT_BLOCK, LBO, SBO), b_hi, idesc, lo_b || c > 0);
-                            umma_commit(smem_u32(empty + stage));  // frees both slots of the stage when these MMAs retire
+                            umma_commit_multicast(smem_u32(empty + stage), (uint16_t)((1u << CL) - 1));   // frees the stage in every CTA
                             if (++stage == p.nstages) { stage = 0; ph ^= 1; }
                         }
                         umma_commit(smem_u32(heads ? heads_full : acc_full));
@@ -201,56 +212,52 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
         uint32_t accph = 0, hph = 0, bfph[2] = {0, 0};
         long long pc[6] = {0, 0, 0, 0, 0, 0}, tl = p.prof ? clock64() : 0;   // [0] board staging [1] one-hot [2] wait acc [3] layer epilogue [5] wait heads of the previous tile
         uint8_t *my_scr = scr + (size_t)(row >> 3) * SBO + (size_t)(row & 7) * 16;      // my row inside every operand block
-        constexpr int MAXW = 22;                                   // words per thread: A <= 169 -> 43 words per row
+        // board staging: two threads per row, each moves half of the row's 4-byte words with cp.async straight into the tile buffer
+        // (no registers held across the tile); the NEXT tile's rows are fetched after this tile's first layer
         const int wpr = (A + 3) / 4, wfirst = (et & 1) ? (wpr + 1) / 2 : 0, wcount = (et & 1) ? wpr / 2 : (wpr + 1) / 2;
         const int srow = et >> 1;
-        uint32_t bw[MAXW];
-        int32_t sv_next = -1;
-        auto fetch_tile = [&](int tile) {                          // issue the loads of `tile`'s board words and seat for row `srow`
+        auto fetch_tile = [&](int tile, int nbuf) {
             const int m = tile * TILE_M + srow;
-            sv_next = -1;
-#pragma unroll
-            for (int k = 0; k < MAXW; k++) bw[k] = 0;
+            int32_t sv = -1;
+            const uint8_t *src = nullptr;
             if (tile < ntiles && m < p.B) {
-                const uint8_t *src = nullptr;
                 if (p.tree_mode) {
                     const int nd = p.tree.leaf[m];
                     if (nd >= 0) {
-                        sv_next = (int32_t)p.tree.node[(size_t)m * p.tree.T + nd].seat | (nd << 8);
+                        sv = (int32_t)p.tree.node[(size_t)m * p.tree.T + nd].seat | (nd << 8);
                         src = p.tree.board + ((size_t)m * p.tree.T + nd) * p.tree.BP;
                     }
                 } else {
-                    sv_next = p.seats[m];
+                    sv = p.seats[m];
                     src = p.board + (size_t)m * p.board_pitch;
                 }
-                if (sv_next >= 0) {
-                    if (p.tree_mode || ((p.board_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(p.board) & 3) == 0)) {
-#pragma unroll
-                        for (int k = 0; k < MAXW; k++)
-                            if (k < wcount) bw[k] = reinterpret_cast<const uint32_t *>(src)[wfirst + k];
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < MAXW; k++)
-                            if (k < wcount)
-                                for (int u = 0; u < 4; u++)
-                                    if ((wfirst + k) * 4 + u < A) bw[k] |= (uint32_t)src[(wfirst + k) * 4 + u] << (8 * u);
+            }
+            uint8_t *dst = btile0 + nbuf * btile_bytes + (size_t)srow * bpitch;
+            if (sv >= 0) {                                         // dead rows: the buffer's content is never looked at
+                if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+                    for (int k = 0; k < wcount; k++)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + (wfirst + k) * 4)), "l"(src + (wfirst + k) * 4) : "memory");
+                } else {
+                    for (int k = 0; k < wcount; k++) {
+                        uint32_t wd = 0;
+                        for (int u = 0; u < 4; u++)
+                            if ((wfirst + k) * 4 + u < A) wd |= (uint32_t)src[(wfirst + k) * 4 + u] << (8 * u);
+                        *reinterpret_cast<uint32_t *>(dst + (wfirst + k) * 4) = wd;
                     }
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if ((et & 1) == 0) tseat0[nbuf * TILE_M + srow] = sv;
         };
-        fetch_tile(blockIdx.x);
+        fetch_tile(blockIdx.x, 0);
         int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        for (int tile0 = tile_first; tile0 < ntiles; tile0 += gridDim.x, it++) {
+            const int tile = tile0 + (int)crank;
             const int buf = it & 1;
             uint8_t *btile = btile0 + buf * btile_bytes;
             int32_t *tseat = tseat0 + buf * TILE_M;
-            if (it >= 2) { mbar_wait(smem_u32(board_free + buf), bfph[buf]); bfph[buf] ^= 1; }
-#pragma unroll
-            for (int k = 0; k < MAXW; k++)
-                if (k < wcount) *reinterpret_cast<uint32_t *>(btile + (size_t)srow * bpitch + (wfirst + k) * 4) = bw[k];
-            if ((et & 1) == 0) tseat[srow] = sv_next;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             epi_barrier();
-            fetch_tile(tile + gridDim.x);
             TCK(0);
             const int m = tile * TILE_M + row;
             const int32_t sv = tseat[row];
@@ -297,33 +304,43 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
                 for (int h = 0; h < W / NI; h++) {
                     // z_old of a unit is fetched (L2) while the previous unit is processed — the first one while the MMAs still run;
                     // the thread that reads a unit is the one that wrote it a layer ago
+                    // z strip layout [unit of 16 columns][4 x 16 bytes][row]: a warp's 16-byte accesses are contiguous (512 B)
                     auto zaddr = [&](int q) {
                         const int col = h * NI + (hh * (NI / 32) + q) * 16;
-                        return zscr + ((size_t)(col / 32) * TILE_M + row) * 32 + (col & 16);
+                        return reinterpret_cast<uint4 *>(zscr) + (size_t)(col / 16) * 4 * TILE_M + row;
                     };
                     uint4 zn4[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) zn4[j] = L > 0 ? __ldcg(reinterpret_cast<const uint4 *>(zaddr(0)) + j) : make_uint4(0, 0, 0, 0);
+                    for (int j = 0; j < 4; j++) zn4[j] = L > 0 ? __ldcg(zaddr(0) + j * TILE_M) : make_uint4(0, 0, 0, 0);
                     mbar_wait(smem_u32(acc_full), accph);
                     accph ^= 1;
                     tc_fence_after();
                     TCK(2);
+                    uint32_t acc_n[16], acl_n[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) acl_n[j] = 0;
+                    tmem_ld16(tmem + lane_base + hh * (NI / 2), acc_n);
+                    if (p.precision == 0) tmem_ld16(tmem + lane_base + LO_COL + hh * (NI / 2), acl_n);
 #pragma unroll 1
                     for (int q = 0; q < NI / 32; q++) {
                         const int lc = (hh * (NI / 32) + q) * 16;      // column inside the half
                         const int col = h * NI + lc;                   // feature column of the unit
-                        float *zrow = zaddr(q);
+                        uint4 *zrow = zaddr(q);
                         uint4 zo[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) zo[j] = zn4[j];
                         if (L > 0 && q + 1 < NI / 32) {
 #pragma unroll
-                            for (int j = 0; j < 4; j++) zn4[j] = __ldcg(reinterpret_cast<const uint4 *>(zaddr(q + 1)) + j);
+                            for (int j = 0; j < 4; j++) zn4[j] = __ldcg(zaddr(q + 1) + j * TILE_M);
                         }
                         uint32_t acc[16], acl[16];
-                        tmem_ld16(tmem + lane_base + lc, acc);
-                        if (p.precision == 0) tmem_ld16(tmem + lane_base + LO_COL + lc, acl);
                         tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) { acc[j] = acc_n[j]; acl[j] = acl_n[j]; }
+                        if (q + 1 < NI / 32) {                           // the next unit's accumulators travel during this unit's arithmetic
+                            tmem_ld16(tmem + lane_base + lc + 16, acc_n);
+                            if (p.precision == 0) tmem_ld16(tmem + lane_base + LO_COL + lc + 16, acl_n);
+                        }
                         const float *zf = reinterpret_cast<const float *>(zo);
                         float zn[16];
 #pragma unroll
@@ -335,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
                         if (L < D) {
 #pragma unroll
                             for (int j = 0; j < 4; j++)
-                                __stcg(reinterpret_cast<uint4 *>(zrow) + j, make_uint4(__float_as_uint(zn[4 * j]), __float_as_uint(zn[4 * j + 1]),
+                                __stcg(zrow + j * TILE_M, make_uint4(__float_as_uint(zn[4 * j]), __float_as_uint(zn[4 * j + 1]),
                                                                                         __float_as_uint(zn[4 * j + 2]), __float_as_uint(zn[4 * j + 3])));
                         }
                         uint32_t hi2[8], lo2[8];
@@ -359,15 +376,19 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
                                 *reinterpret_cast<uint4 *>(dst + ACT_BLOCK) = make_uint4(lo2[4 * u], lo2[4 * u + 1], lo2[4 * u + 2], lo2[4 * u + 3]);
                         }
                     }
-                    // the accumulators are drained: the next half's (or the heads') MMAs may overwrite them
+                    // the accumulators are drained: the next half's (or the heads') MMAs may overwrite them; this half of the next
+                    // operand is published
                     tc_fence_before();
+                    fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(tmem_free));
+                    if (lane == 0) { mbar_arrive(smem_u32(tmem_free)); mbar_arrive(smem_u32(a_ready)); }
                     TCK(3);
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(a_ready));
+                if (L == 0) {
+                    // the next tile's boards: its buffer was the previous tile's, and the heads group is done with that one by now
+                    if (it >= 1) { mbar_wait(smem_u32(board_free + (buf ^ 1)), bfph[buf ^ 1]); bfph[buf ^ 1] ^= 1; }
+                    fetch_tile(tile + gridDim.x, buf ^ 1);
+                }
             }
         }
         if (p.prof && threadIdx.x == 0) for (int k = 0; k < 6; k++) atomicAdd(p.prof + 20 + k, (unsigned long long)pc[k]);
@@ -383,10 +404,11 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(oh_ready));            // the first tile needs no hand-over of z
         int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        for (int tile0 = tile_first; tile0 < ntiles; tile0 += gridDim.x, it++) {
+            const int tile = tile0 + (int)crank;
             const int buf = it & 1;
             const uint8_t *brow = btile0 + buf * btile_bytes + (size_t)row * bpitch;
-            const bool last = tile + (int)gridDim.x >= ntiles;
+            const bool last = tile0 + (int)gridDim.x >= ntiles;
             mbar_wait(smem_u32(heads_full), hph);
             hph ^= 1;
             tc_fence_after();
@@ -511,12 +533,13 @@ __global__ void __launch_bounds__(THREADS, 1) fc_tc_wide_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync();                                                // no peer multicasts into a CTA that has left
     if (warp == WARP_MMA) tmem_dealloc(tmem, 512);
 }
 
 int grid_for(int B) {
-    const int ntiles = (B + TILE_M - 1) / TILE_M;
-    return ntiles < BL_NUM_SMS ? ntiles : BL_NUM_SMS;
+    const int ntiles = ((B + TILE_M - 1) / TILE_M + CL - 1) / CL * CL;
+    return ntiles < BL_NUM_SMS / CL * CL ? ntiles : BL_NUM_SMS / CL * CL;
 }
 
 int launch(const bl_fc_params *p, WideParams &k, int B, void *scratch, cudaStream_t st) {
