@@ -379,15 +379,31 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
         // ---- C: child terms of this pass (full divisions), parked at their positions ----------------------------------------
         if (state == ST_PASS || state == ST_FINAL) {
             bool bad = false;
-            for (int i = 0; i < nc; i++) {
-                const ChildEntry e = get(i);
-                const float bot = __fsub_rn(alpha, e.q), bb = __fmul_rn(bot, bot);
-                const float s = bl_div_fast(e.top, bot), g = bl_div_fast(-e.top, bb);
-                ps[e.a] = s;
-                pg[e.a] = g;
-                // bot outside [2^-60, 2^60] (never seen; alpha > q by construction) leaves the branch-free division's safe range;
-                // a negative / non-finite term would also break the monotone running sums: both go to the exact serial path
-                bad |= !(bot >= 8.67e-19f && bot <= 1.15e18f) || !(s >= 0.f && s <= 3.0e38f);
+            // BL_CHILD_ILP children per step: their division chains are independent, and the loop is latency-bound (a short tail
+            // recomputes the last child); measured on c2: 1 per step 15.6, 2 per step 14.4, 4 per step 14.95 ms per move
+#ifndef BL_CHILD_ILP
+#define BL_CHILD_ILP 2
+#endif
+            for (int i = 0; i < nc; i += BL_CHILD_ILP) {
+                ChildEntry e[BL_CHILD_ILP];
+                float bot[BL_CHILD_ILP], sv[BL_CHILD_ILP], gv[BL_CHILD_ILP];
+#pragma unroll
+                for (int u = 0; u < BL_CHILD_ILP; u++) e[u] = get(i + u < nc ? i + u : nc - 1);
+#pragma unroll
+                for (int u = 0; u < BL_CHILD_ILP; u++) {
+                    bot[u] = __fsub_rn(alpha, e[u].q);
+                    const float bb = __fmul_rn(bot[u], bot[u]);
+                    sv[u] = bl_div_fast(e[u].top, bot[u]);
+                    gv[u] = bl_div_fast(-e[u].top, bb);
+                }
+#pragma unroll
+                for (int u = 0; u < BL_CHILD_ILP; u++) {
+                    ps[e[u].a] = sv[u];
+                    pg[e[u].a] = gv[u];
+                    // bot outside [2^-60, 2^60] (never seen; alpha > q by construction) leaves the branch-free division's safe range;
+                    // a negative / non-finite term would also break the monotone running sums: both go to the exact serial path
+                    bad |= !(bot[u] >= 8.67e-19f && bot[u] <= 1.15e18f) || !(sv[u] >= 0.f && sv[u] <= 3.0e38f);
+                }
             }
             if (bad) state = ST_SLOW;
         }
@@ -525,6 +541,7 @@ unsigned long long *g_phase_prof = nullptr;
 bool g_last_fused = false;
 // service gate (see the kernel): BL_GATE="num/den" in the environment overrides the default for tuning runs
 int g_gate_num = BL_GATE_NUM, g_gate_den = BL_GATE_DEN;
+int g_grid_limit = 0;      // BL_DESCEND_GRID: cap on the number of warps (fewer lanes than envs: lanes pull envs from the queue)
 void read_gate_env() {
     static bool done = false;
     if (done) return;
@@ -533,6 +550,7 @@ void read_gate_env() {
         int a = 0, b = 0;
         if (sscanf(e, "%d/%d", &a, &b) == 2 && a >= 0 && b > 0) { g_gate_num = a; g_gate_den = b; }
     }
+    if (const char *e = getenv("BL_DESCEND_GRID")) g_grid_limit = atoi(e);
 }
 
 template <int NCH, bool PROF>
@@ -549,7 +567,8 @@ int launch_v3p(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, i
         if (occ < 1) { occ = 0; return -2; }
     }
     const int need = (t->B + 31) / 32;
-    const int grid = need < occ * BL_NUM_SMS ? need : occ * BL_NUM_SMS;
+    int grid = need < occ * BL_NUM_SMS ? need : occ * BL_NUM_SMS;
+    if (g_grid_limit > 0 && grid > g_grid_limit) grid = g_grid_limit;
     if ((int64_t)grid * 32 * cap * (int64_t)sizeof(ChildEntry) > t->scratch_bytes) return -3;
     // every env resident (one per lane) and the lane's rows big enough for a board + flood-fill stack: expand in the same kernel
     const bool fused = (long long)grid * 32 >= t->B && t->BP <= 4 * 4 * NCH;
