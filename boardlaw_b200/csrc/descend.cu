@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
     // copy of the env's parent row (scanned at every visit)
     constexpr int NW = (PS + 63) / 64;                  // 64-bit words of the child-position mask
     constexpr int MW = 4;                               // 64-bit words of the children-of-this-node mask (T <= 256; else list walk)
-    constexpr int STEP0 = PS >= 128 ? 128 : (PS >= 64 ? 64 : (PS >= 32 ? 32 : (PS >= 16 ? 16 : 8)));
+    constexpr int SEG = PS > 144 ? 14 : (PS > 100 ? 12 : (PS > 64 ? 10 : (PS > 36 ? 8 : (PS > 16 ? 6 : 4))));   // SEG*SEG >= PS >= A
     extern __shared__ float4 smem4[];
     const int A = t.A, T = t.T;
     const int lane = threadIdx.x;
@@ -199,12 +199,21 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                 // every term is >= 0 (checked for child terms in C), so the sums are non-decreasing: first index with sum >= r.
                 // The reference additionally skips p == 0 entries: the first hit can only have p == 0 when r == 0 (then the
                 // answer is the first nonzero entry), and when no sum reaches r the answer is the last nonzero entry.
-                int l = 0;
+                // l = #{a : sum[a] < r}, counted in two rounds of INDEPENDENT loads (segment ends, then the hit segment's entries)
+                // instead of a binary search's log2(A) dependent ones
+                int c1 = 0;
 #pragma unroll
-                for (int step = STEP0; step; step >>= 1) {
-                    const int np = l + step;
-                    if (np <= A && ps[np - 1] < r) l = np;
+                for (int j = 0; j < SEG; j++) {
+                    const int e = (j + 1) * SEG < A ? (j + 1) * SEG : A;        // exclusive end of segment j (empty ones repeat A)
+                    c1 += (j * SEG < A && ps[e - 1] < r) ? 1 : 0;
                 }
+                int l = c1 * SEG;
+                if (l < A) {
+                    int c2 = 0;
+#pragma unroll
+                    for (int j = 0; j < SEG - 1; j++) c2 += (l + j < A && ps[l + j] < r) ? 1 : 0;   // the segment's last entry is >= r
+                    l += c2;
+                } else l = A;
                 const int first_nz = nzpos & 255, last_nz = (nzpos >> 8) & 255;
                 action = first_nz == 255 ? -1 : (l < A ? (r <= 0.f ? first_nz : l) : last_nz);
                 state = ST_ADVANCE;

@@ -1,3 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for g in 1/2 2/5 3/5; do echo "gate $g $(BL_GATE=$g timeout 300 python tools/descend_phases.py c2 2>&1 | grep -E "plain")"; done
+timeout 900 python -m pytest tests/test_gpu_mcts.py tests/test_gpu_agent.py -m gpu -q --no-header -rN --tb=short -x 2>&1 | tail -5
+timeout 300 python tools/descend_phases.py c2 2>&1 | grep -E "plain|sample|pass  "
+timeout 300 python tools/descend_phases.py c5-13 2>&1 | grep -E "plain"
