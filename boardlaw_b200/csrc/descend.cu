@@ -74,6 +74,7 @@ __device__ __forceinline__ void bl_expand_one(const bl_tree &t, int sim, int b, 
         ln.n = 0; ln.w[0] = 0; ln.w[1] = 0;
         t.node[node0 + parent].first_child = (int16_t)sim;
         t.parent_of[(size_t)b * ((T + 7) & ~7) + sim] = (int16_t)parent;
+        t.kids[(node0 + parent) * ((T + 63) >> 6) + (sim >> 6)] |= 1ull << (sim & 63);
         t.leaf[b] = (int16_t)leaf;
     } else {                                                    // stopped at an existing terminal child: reuse its slot
         ln = bl_ld_node(t.node + node0 + leaf);
@@ -115,8 +116,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                                                         ChildEntry *__restrict__ clists, int cap, unsigned long long *prof,
                                                         int gate_num, int gate_den, int fuse_expand) {
     constexpr int PS = 4 * NCH;                         // row pitch in floats; NCH odd => conflict-free 128-bit lane-private rows
-    // the lane's third shared-memory row holds its child entries (16 B each; the rest go to global scratch) and, when it fits, a
-    // copy of the env's parent row (scanned at every visit)
+    // the lane's third shared-memory row holds its child entries (16 B each; the rest go to global scratch)
     constexpr int NW = (PS + 63) / 64;                  // 64-bit words of the child-position mask
     constexpr int MW = 4;                               // 64-bit words of the children-of-this-node mask (T <= 256; else list walk)
     constexpr int SEG = PS > 144 ? 14 : (PS > 100 ? 12 : (PS > 64 ? 10 : (PS > 36 ? 8 : (PS > 16 ? 6 : 4))));   // SEG*SEG >= PS >= A
@@ -134,13 +134,10 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
     const uint64_t keep = bl_policy_keep();
     int *queue = reinterpret_cast<int *>(t.counters + C_QUEUE);
     const int nrow4 = t.AP >> 2;
-    const int TP = (T + 7) & ~7;
+    const int KW = (T + 63) >> 6;                     // 64-bit words of a node's children mask (t.kids)
     const bool scan_ok = T <= 64 * MW;
-    const bool pcache = scan_ok && TP * 2 + 5 * 16 <= PS * 4;      // parent row cached in shared memory, >= 5 entry slots left
-    const int KS = pcache ? (PS * 4 - TP * 2) / 16 : NCH;
-    const uint4 *pc4 = reinterpret_cast<const uint4 *>(pe4 + KS);
-    const uint32_t pc_addr = pe_addr + 16u * KS;
-    const int nscan = (sim + 7) >> 3;                 // 16-byte chunks of the parent row that can hold nodes created so far
+    constexpr int KS = NCH;                           // child entries held in the lane's third shared-memory row; the rest spill
+                                                      // to global scratch
 
     u64 tp[2 * NCH];                                  // lambda*pi of the current node, element pairs
     u64 cm[NW];                                       // bit a set: action a has a child
@@ -180,6 +177,9 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
     auto prefetch_node = [&](int n) {
         const size_t slot = (size_t)b * T + n;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pg_addr), "l"(t.aux + slot) : "memory");       // row summary -> pg[0..3]
+        if (scan_ok)                                                                                                    // children mask -> pg[4..]
+            for (int w = 0; w < KW; w++)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pg_addr + 16u + 8u * w), "l"(t.kids + slot * KW + w) : "memory");
         const float4 *row = reinterpret_cast<const float4 *>(t.pi + slot * t.AP);
 #pragma unroll
         for (int c = 0; c < NCH; c++)
@@ -261,12 +261,6 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                         if (root.terminal) state = ST_DONE;       // a terminal root ends the descent at the next service (leaf = 0, no action)
                         else {
                             state = ST_VISIT;
-                            if (pcache) {                          // its own (older) group: the visit waits for it alone first
-                                for (int k = 0; k < (TP >> 3); k++)
-                                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pc_addr + 16u * k),
-                                                 "l"(t.parent_of + (size_t)b * TP + 8 * k) : "memory");
-                                asm volatile("cp.async.commit_group;" ::: "memory");
-                            }
                             prefetch_node(0);
                         }
                     }
@@ -295,31 +289,12 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
                     nc++;
                 };
                 if (scan_ok) {
-                    // children = the nodes whose parent is `cur`: one scan of the env's parent row (independent 16-byte loads)
-                    // instead of a walk down the sibling list (one dependent load per child); their records are then fetched
-                    // together by cp.async straight into the lane's entry slots
-                    if (pcache) asm volatile("cp.async.wait_group 1;" ::: "memory");       // the parent row (older group); the pi row may still fly
-                    const uint4 *prow = reinterpret_cast<const uint4 *>(t.parent_of + (size_t)b * TP);
-                    const uint32_t cur2 = (uint32_t)cur * 0x10001u;
+                    // children = the bits of the node's mask, landed with its row summary; their records are then fetched together
+                    // by cp.async straight into the lane's entry slots
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                     u64 mm[MW];
 #pragma unroll
-                    for (int w = 0; w < MW; w++) {
-                        u64 m64 = 0;
-                        if (w * 8 < nscan) {
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                if (w * 8 + j < nscan) {
-                                    const uint4 pv = pcache ? pc4[w * 8 + j] : bl_ld16_hint(prow + w * 8 + j, keep);
-                                    const uint32_t e0 = __vcmpeq2(pv.x, cur2), e1 = __vcmpeq2(pv.y, cur2), e2 = __vcmpeq2(pv.z, cur2),
-                                                   e3 = __vcmpeq2(pv.w, cur2);
-                                    const uint32_t m8 = ((e0 & 1u) | ((e0 >> 15) & 2u)) | (((e1 & 1u) | ((e1 >> 15) & 2u)) << 2) |
-                                                        (((e2 & 1u) | ((e2 >> 15) & 2u)) << 4) | (((e3 & 1u) | ((e3 >> 15) & 2u)) << 6);
-                                    m64 |= (u64)m8 << (8 * j);
-                                }
-                            }
-                        }
-                        mm[w] = m64;
-                    }
+                    for (int w = 0; w < MW; w++) mm[w] = w < KW ? *reinterpret_cast<const u64 *>(pg + 4 + 2 * w) : 0ull;
                     tick(7);
                     int k = 0;
 #pragma unroll

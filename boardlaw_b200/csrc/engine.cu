@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) reset_kernel(bl_tree t, const uint8_t *__
     }
     const int TP = (t.T + 7) & ~7;
     for (long long i = i0; i < (long long)t.B * TP; i += stride) t.parent_of[i] = -1;
+    for (long long i = i0; i < BT * ((t.T + 63) >> 6); i += stride) t.kids[i] = 0ull;
     for (long long i = i0; i < t.B; i += stride) t.c_puct[i] = c_puct;
     int *qr = reinterpret_cast<int *>(t.qrange);
     for (long long i = i0; i <= t.T; i += stride) {

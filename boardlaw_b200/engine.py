@@ -39,7 +39,7 @@ class SearchEngine:
         self.ws = arrdict.arrdict(
             pi=z((B, T, self.AP), torch.float32),
             board=z((B, T, self.BP), torch.uint8),
-            node=node, aux=aux, parent_of=z((B, _round_up(T, 8)), torch.int16),
+            node=node, aux=aux, parent_of=z((B, _round_up(T, 8)), torch.int16), kids=z((B, T, (T + 63) // 64), torch.int64),
             c_puct=z((B,), torch.float16),
             leaf=z((B,), torch.int16), leaf_parent=z((B,), torch.int16), leaf_action=z((B,), torch.int16),
             leaf_v=z((B, Sn), torch.float16),

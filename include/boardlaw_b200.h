@@ -185,7 +185,9 @@ typedef struct bl_tree {
     bl_node *node;        /* (B,T)                                                                  */
     bl_aux *aux;          /* (B,T)                                                                  */
     int16_t *parent_of;   /* (B,TP) i16, TP = T rounded up to a multiple of 8: parent of every node (-1 = none) as one
-                             contiguous row per env — the descent finds a node's children by scanning it             */
+                             contiguous row per env (trees deeper than the kids masks cover walk the sibling lists)   */
+    uint64_t *kids;       /* (B,T,KW) u64, KW = ceil(T/64): bit k of a node's mask = node k is its child; set by the expand step,
+                             read by the descent's visit (one 8*KW-byte fetch instead of a scan of parent_of)           */
     bl_half *c_puct;      /* (B,)   half                                                            */
     int16_t *leaf;        /* (B,)   i16 leaf of the current simulation                              */
     int16_t *leaf_parent; /* (B,)   i16                                                             */
