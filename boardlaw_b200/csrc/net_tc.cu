@@ -39,7 +39,7 @@ constexpr int WARP_LOAD = 12, WARP_MMA = 13;
 constexpr int TC_THREADS = 448;
 constexpr int AH_COL = 256, AL_COL = 384;  // TMEM columns of the activation operand (hi, lo)
 constexpr int MAX_STAGES = 8;
-constexpr int HEADS_REG_COLS = 96;         // head columns an IO thread can hold in registers (Np <= 96: S <= 9)
+constexpr int VGROUPS = 16;                // 16-cell groups of legal-move bits per row (A <= 256)
 
 struct TcParams {
     const uint8_t *board;                  // env e's board at board + e*board_pitch (absolute frame, A bytes); tree mode: tree.board
@@ -69,7 +69,8 @@ __host__ __device__ inline Shape make_shape(int W, int K0p, int Np) {
 __host__ __device__ inline int board_pitch_bytes(int A) { return 4 * (((A + 3) / 4) | 1); }   // odd number of words: conflict-free rows
 size_t bias_bytes(int W, int D, int Np) { return ((size_t)(D + 1) * W + Np) * sizeof(float); }
 size_t smem_bytes(const Shape &s, int nstages, int A, int W, int D, int Np) {
-    return (size_t)s.stage_bytes * nstages + 2 * (size_t)TILE_M * board_pitch_bytes(A) + 1024 + 2 * TILE_M * sizeof(int32_t) + bias_bytes(W, D, Np);
+    return (size_t)s.stage_bytes * nstages + 2 * (size_t)TILE_M * board_pitch_bytes(A) + 1024 + 2 * TILE_M * sizeof(int32_t) +
+           2 * TILE_M * VGROUPS * sizeof(uint16_t) + bias_bytes(W, D, Np);
 }
 
 #define TCK(k) do { if (p.prof) { const long long now_ = clock64(); pc[k] += now_ - tl; tl = now_; } } while (0)
@@ -86,12 +87,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
              *heads_full = a_ready + 3, *board_free = a_ready + 4;   // board_free[2]
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(a_ready + 6);
     int32_t *tseat0 = reinterpret_cast<int32_t *>(tmem_ptr + 4);  // [2][TILE_M] seat | node << 8 of the tiles' rows
-    float *sbias = reinterpret_cast<float *>(tseat0 + 2 * TILE_M); // (D+1, W) cumulative biases, then the head bias (Np)
+    uint16_t *vmask0 = reinterpret_cast<uint16_t *>(tseat0 + 2 * TILE_M);   // [2][TILE_M][VGROUPS] legal-move bits of the tiles' rows, 16 cells per entry
+    float *sbias = reinterpret_cast<float *>(vmask0 + 2 * TILE_M * VGROUPS); // (D+1, W) cumulative biases, then the head bias (Np)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.W, D = p.D, A = p.A, S = p.S, Np = p.Np, K0p = p.K0p;
     const int ntiles = (p.B + TILE_M - 1) / TILE_M;
-    const bool heads_in_regs = Np <= HEADS_REG_COLS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nstages; s++) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                 const uint32_t own_mask = seat ? 0x64u : 0x1Au, opp_mask = seat ? 0x1Au : 0x64u;
                 int r = cb / S, c = cb - r * S;                    // (row, col) of cell `cb`
                 for (int j0 = 0; j0 < my_cols; j0 += 16) {
-                    uint32_t wds[16];
+                    uint32_t wds[16], vbits16 = 0;
 #pragma unroll
                     for (int u = 0; u < 16; u++) {
                         const int cell = cb + j0 + u;
@@ -274,11 +275,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                         if (live && cell < A) {
                             const uint32_t cv = brow[seat ? c * S + r : cell];
                             wd = ((own_mask >> cv) & 1u) * 0x3C00u | ((opp_mask >> cv) & 1u) * 0x3C000000u;      // fp16 1.0
+                            vbits16 |= (wd == 0u ? 1u : 0u) << u;      // neither side's stone: a legal move (heads.py:101)
                         }
                         wds[u] = wd;
                         if (++c == S) { c = 0; r++; }
                     }
                     tmem_st16(tmem + lane_base + AH_COL + cb + j0, wds);
+                    // the heads group reads the legal-move bits instead of walking the board again
+                    vmask0[((size_t)buf * TILE_M + row) * VGROUPS + ((cb + j0) >> 4)] = (uint16_t)vbits16;
                 }
                 tmem_wait_st();
                 tc_fence_before();
@@ -352,74 +356,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
             const int32_t sv = tseat0[buf * TILE_M + row];
             const bool live = m < p.B && sv >= 0;
             const int seat = live ? (sv & 1) : 0;
-            float x[HEADS_REG_COLS];                               // raw head outputs of my row (fast path)
-            if (heads_in_regs) {
-#pragma unroll
-                for (int u = 0; u < HEADS_REG_COLS / 16; u++) {
-                    if (u < nu) {
-                        uint32_t acc[16];
-                        tmem_ld16(tmem + lane_base + u * 16, acc);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 16; j++) x[u * 16 + j] = __uint_as_float(acc[j]) + bh[u * 16 + j];
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0 && !last) mbar_arrive(smem_u32(oh_ready));      // z is free: the next tile's layer 0 may overwrite it
-            }
             TCK(2);
-            // legal moves (cell empty) of my row as a bitmask over head columns
-            unsigned long long vm[3] = {0, 0, 0};
-            {
-                int r = 0, c = 0;
-                for (int a = 0; a < A; a++) {
-                    const unsigned long long bit = brow[seat ? c * S + r : a] == BL_EMPTY ? 1ull : 0ull;
-                    vm[a >> 6] |= bit << (a & 63);
-                    if (++c == S) { c = 0; r++; }
-                }
-            }
-            auto vbits = [&](int u) { return (uint32_t)((vm[(u * 16) >> 6] >> ((u * 16) & 63)) & 0xFFFFull); };
-            auto unit = [&](int u, float (&y)[16]) {                // raw head outputs of columns [16u, 16u+16)
-                if (heads_in_regs) {
-#pragma unroll
-                    for (int uu = 0; uu < HEADS_REG_COLS / 16; uu++)
-                        if (uu == u) {
-#pragma unroll
-                            for (int j = 0; j < 16; j++) y[j] = x[uu * 16 + j];
-                        }
-                } else {
-                    uint32_t acc[16];
-                    tmem_ld16(tmem + lane_base + u * 16, acc);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; j++) y[j] = __uint_as_float(acc[j]) + bh[u * 16 + j];
-                }
+            // legal moves of my row, 16 cells per entry, left by the layer group beside the one-hot operand (the value column and the
+            // padding columns read as illegal).  The accumulator row stays in tensor memory and each pass below re-reads it unit by
+            // unit: a register copy of the row would have to be indexed by the (runtime) unit number, i.e. live in local memory, and the
+            // L1 left beside 225 KB of shared memory does not hold 128 such rows — measured, that version spent 58k cycles per tile here.
+            const uint4 *vrow = reinterpret_cast<const uint4 *>(vmask0 + ((size_t)buf * TILE_M + row) * VGROUPS);
+            const uint4 va = vrow[0], vc = vrow[1];
+            auto vbits = [&](int u) {
+                const uint32_t wsel = (u >> 1) == 0 ? va.x : (u >> 1) == 1 ? va.y : (u >> 1) == 2 ? va.z : (u >> 1) == 3 ? va.w
+                                    : (u >> 1) == 4 ? vc.x : (u >> 1) == 5 ? vc.y : (u >> 1) == 6 ? vc.z : vc.w;
+                const uint32_t bits = (u & 1) ? wsel >> 16 : wsel & 0xFFFFu;
+                // cells past A (value column, padding) are never legal; groups the one-hot stage did not cover hold stale bits
+                const int rem = A - u * 16;
+                return rem >= 16 ? bits : (rem <= 0 ? 0u : bits & ((1u << rem) - 1u));
             };
+            // raw head outputs of columns [16u, 16u+16); the NEXT unit's accumulators travel from tensor memory meanwhile
+            uint32_t nxt[16];
+            auto unit = [&](int u, float (&y)[16]) {
+                tmem_wait_ld();
+                uint32_t acc[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) acc[j] = nxt[j];
+                tmem_ld16(tmem + lane_base + (u + 1 < nu ? u + 1 : 0) * 16, nxt);       // (wraps to unit 0: the next pass starts there)
+#pragma unroll
+                for (int j = 0; j < 16; j++) y[j] = __uint_as_float(acc[j]) + bh[u * 16 + j];
+            };
+            tmem_ld16(tmem + lane_base, nxt);
             TCK(3);
-            // pass 1: max over the legal actions; the value head's column sits right after the policy's
-            float mx = -BL_INF_F, tanh_v = 0.f;
+            // pass 1: max and sum of exp over the legal actions in ONE sweep (running max, sum rescaled when it moves); the value
+            // head's column sits right after the policy's
+            float mx = -BL_INF_F, sum = 0.f, vraw = 0.f;
             for (int u = 0; u < nu; u++) {
                 float y[16];
                 unit(u, y);
                 const uint32_t vb = vbits(u);
+                float m0 = -BL_INF_F, m1 = -BL_INF_F;
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    if ((vb >> j) & 1u) mx = fmaxf(mx, y[j]);
-                    if (u * 16 + j == A) tanh_v = tanhf(y[j]);
+                for (int j = 0; j < 16; j += 2) {
+                    m0 = fmaxf(m0, ((vb >> j) & 1u) ? y[j] : -BL_INF_F);
+                    m1 = fmaxf(m1, ((vb >> (j + 1)) & 1u) ? y[j + 1] : -BL_INF_F);
+                    if (u * 16 + j == A) vraw = y[j];
+                    if (u * 16 + j + 1 == A) vraw = y[j + 1];
+                }
+                const float mn = fmaxf(mx, fmaxf(m0, m1));
+                if (mn > -BL_INF_F) {                              // (all-illegal so far: nothing to add, and -inf - -inf is NaN)
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        if ((vb >> j) & 1u) s0 += __expf(y[j] - mn);
+                        if ((vb >> (j + 1)) & 1u) s1 += __expf(y[j + 1] - mn);
+                    }
+                    sum = sum * __expf(mx - mn) + (s0 + s1);       // exp(-inf) = 0 on the first legal unit
+                    mx = mn;
                 }
             }
+            const float tanh_v = tanhf(vraw);
             TCK(4);
-            // pass 2: sum of exp
-            float sum = 0.f;
-            for (int u = 0; u < nu; u++) {
-                float y[16];
-                unit(u, y);
-                const uint32_t vb = vbits(u);
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if ((vb >> j) & 1u) sum += __expf(y[j] - mx);
-            }
             const float lse = logf(sum);
             TCK(5);
             // pass 3 — tree mode: logits -> half -> exp table -> pi row + row summary, straight into the search tree (what
@@ -461,6 +454,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                     }
                 }
             }
+            tmem_wait_ld();                                        // (the wrapped prefetch of the last unit)
             if (live) {
                 const float v0 = seat ? -tanh_v : tanh_v, v1 = -v0;
                 if (p.tree_mode) {
@@ -477,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (!heads_in_regs && !last) mbar_arrive(smem_u32(oh_ready));  // slow path: z was needed until now
+                if (!last) mbar_arrive(smem_u32(oh_ready));                    // z was needed until now
                 mbar_arrive(smem_u32(board_free + buf));
             }
             TCK(6);
