@@ -12,6 +12,7 @@
 // warp-cooperative coalesced row loads into lane-major shared-memory columns (odd pitch => conflict-free both ways).
 //
 // Compiled with -fmad=false -prec-div=true -ftz=false (see build.py).
+#include <cstdlib>
 #include "engine_internal.cuh"
 #include "hex_core.cuh"
 #include "mcts_core.cuh"
@@ -190,53 +191,63 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
 }
 
 // ---- backup + q-range scan ----------------------------------------------------------------------------------------
-// One warp per env: the env's node records 0..sim (16 B each, contiguous) are staged in shared memory with coalesced loads,
-// lane 0 walks the leaf->root path there (shared-memory latency per step instead of a DRAM round trip), the touched records
-// are written back, and the same staged records feed the (min,max) of w/(n+1e-4) that the NEXT descent normalises with
-// (slot sim+1).  Rewards are +-1 for the winner's code stored in the record's `terminal` byte (0 = not terminal).
-constexpr int BK_WARPS = 8;
+// One CTA per group of up to 32 envs, one warp per env: the env's node records 0..sim (16 B each, contiguous) are staged in
+// shared memory with coalesced loads; then WARP 0 walks the leaf->root paths of all the CTA's envs at once, one lane per env,
+// in the staged copies (shared-memory latency per step instead of a DRAM round trip, and 32 active lanes instead of one — the
+// walk is ~60 dependent instructions per path node, which at one lane per warp made the kernel issue-bound); each warp then
+// writes its env's touched records back and the same staged records feed the (min,max) of w/(n+1e-4) that the NEXT descent
+// normalises with (slot sim+1).  Rewards are +-1 for the winner's code stored in the record's `terminal` byte (0 = not terminal).
+constexpr int BK_WARPS = 32;
 __global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int sim, int warps) {
     extern __shared__ uint4 bsm[];
     __shared__ int red[2 * BK_WARPS];
     const int T = t.T, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * warps + warp;
     const int nrec = sim + 1;                                   // node slots that can be populated so far
-    uint4 *rec = bsm + (size_t)warp * (T + ((T + 31) >> 5));    // T records, then a dirty bitmask (one word per 32 nodes)
+    const int stride = T + ((T + 31) >> 5);                     // per env: T records, then a dirty bitmask (one word per 32 nodes)
+    uint4 *rec = bsm + (size_t)warp * stride;
     uint32_t *dirty = reinterpret_cast<uint32_t *>(rec + T);
-    float lo = BL_INF, hi = -BL_INF;
-    unsigned visited = 0;
-    if (b < t.B) {
-        uint4 *g = reinterpret_cast<uint4 *>(t.node + (size_t)b * T);
+    uint4 *g = reinterpret_cast<uint4 *>(t.node + (size_t)(b < t.B ? b : 0) * T);
+    // warp 0, lane l: the leaf and its value of the CTA's env l (loaded while the records travel)
+    int leaf = -1;
+    float val[2] = {0.f, 0.f};
+    if (warp == 0 && lane < warps && blockIdx.x * warps + lane < t.B) {
+        const int bl = blockIdx.x * warps + lane;
+        leaf = t.leaf[bl];
+        const uint32_t lv = reinterpret_cast<const uint32_t *>(t.leaf_v)[bl];        // = aux[leaf].v, without the dependent load
+        if (leaf >= 0) { val[0] = bl_h2f((bl_half)(lv & 0xFFFF)); val[1] = bl_h2f((bl_half)(lv >> 16)); }
+    }
+    if (warp < warps && b < t.B) {
         for (int k = lane; k < nrec; k += 32) rec[k] = g[k];
         for (int k = lane; k < ((T + 31) >> 5); k += 32) dirty[k] = 0;
-        int leaf = -1;
-        float val[2] = {0.f, 0.f};
-        if (lane == 0) {
-            leaf = t.leaf[b];
-            const uint32_t lv = reinterpret_cast<const uint32_t *>(t.leaf_v)[b];     // = aux[leaf].v, without the dependent load
-            if (leaf >= 0) { val[0] = bl_h2f((bl_half)(lv & 0xFFFF)); val[1] = bl_h2f((bl_half)(lv >> 16)); }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            for (int cur = leaf; cur >= 0;) {
-                union { uint4 u; bl_node n; } x;
-                x.u = rec[cur];
-                const float r0 = x.n.terminal == 1 ? 1.f : (x.n.terminal == 2 ? -1.f : 0.f);
-                const float rw[2] = {r0, x.n.terminal == 1 ? -1.f : (x.n.terminal == 2 ? 1.f : 0.f)};      // +0, never -0
+    }
+    __syncthreads();
+    unsigned visited = 0;
+    if (warp == 0) {
+        uint4 *myrec = bsm + (size_t)lane * stride;
+        uint32_t *mydirty = reinterpret_cast<uint32_t *>(myrec + T);
+        for (int cur = leaf; cur >= 0;) {
+            union { uint4 u; bl_node n; } x;
+            x.u = myrec[cur];
+            const float r0 = x.n.terminal == 1 ? 1.f : (x.n.terminal == 2 ? -1.f : 0.f);
+            const float rw[2] = {r0, x.n.terminal == 1 ? -1.f : (x.n.terminal == 2 ? 1.f : 0.f)};      // +0, never -0
 #pragma unroll
-                for (int s = 0; s < 2; s++) {
-                    if (x.n.terminal) val[s] = 0.f;
-                    val[s] = __fadd_rn(val[s], rw[s]);
-                    x.n.w[s] = bl_f2h(__fadd_rn(bl_h2f(x.n.w[s]), bl_h2f(bl_f2h(val[s]))));
-                }
-                x.n.n = (int16_t)(x.n.n + t.Sn);                    // quirk: +1 per seat (cuda.cu:228)
-                rec[cur] = x.u;
-                dirty[cur >> 5] |= 1u << (cur & 31);
-                cur = x.n.parent;
-                visited++;
+            for (int s = 0; s < 2; s++) {
+                if (x.n.terminal) val[s] = 0.f;
+                val[s] = __fadd_rn(val[s], rw[s]);
+                x.n.w[s] = bl_f2h(__fadd_rn(bl_h2f(x.n.w[s]), bl_h2f(bl_f2h(val[s]))));
             }
+            x.n.n = (int16_t)(x.n.n + t.Sn);                    // quirk: +1 per seat (cuda.cu:228)
+            myrec[cur] = x.u;
+            mydirty[cur >> 5] |= 1u << (cur & 31);
+            cur = x.n.parent;
+            visited++;
         }
-        __syncwarp();
+        visited = __reduce_add_sync(0xffffffffu, visited);
+    }
+    __syncthreads();
+    float lo = BL_INF, hi = -BL_INF;
+    if (warp < warps && b < t.B) {
         for (int k = lane; k < nrec; k += 32) {
             union { uint4 u; bl_node n; } x;
             x.u = rec[k];
@@ -250,14 +261,16 @@ __global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int si
     const int klo = __reduce_min_sync(0xffffffffu, bl_f2ord(lo)), khi = __reduce_max_sync(0xffffffffu, bl_f2ord(hi));
     if (lane == 0) { red[warp] = klo; red[BK_WARPS + warp] = khi; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int a = red[0], c = red[BK_WARPS];
-        for (int w = 1; w < warps; w++) { a = min(a, red[w]); c = max(c, red[BK_WARPS + w]); }
-        int *qr = reinterpret_cast<int *>(t.qrange) + 2 * (sim + 1);
-        atomicMin(qr, a);
-        atomicMax(qr + 1, c);
+    if (warp == 0) {
+        const int a = __reduce_min_sync(0xffffffffu, lane < warps ? red[lane] : bl_f2ord(BL_INF));
+        const int c = __reduce_max_sync(0xffffffffu, lane < warps ? red[BK_WARPS + lane] : bl_f2ord(-BL_INF));
+        if (lane == 0) {
+            int *qr = reinterpret_cast<int *>(t.qrange) + 2 * (sim + 1);
+            atomicMin(qr, a);
+            atomicMax(qr + 1, c);
+            if (visited) atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_BACKUP_NODES), (unsigned long long)visited);
+        }
     }
-    if (lane == 0 && visited) atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_BACKUP_NODES), (unsigned long long)visited);
 }
 
 // ---- root ------------------------------------------------------------------------------------------------------------
@@ -410,6 +423,11 @@ extern "C" int bl_tree_backup(const bl_tree *t, int sim, bl_stream stream) {
     int warps = (int)(200 * 1024 / per_warp);
     if (warps < 1) return -2;
     if (warps > BK_WARPS) warps = BK_WARPS;
+    // envs per CTA: the phases (stage, walk, write back) are latency-bound, so small CTAs that overlap each other beat full
+    // walker warps — measured on c2: 32 envs 1.56, 16 envs 1.45, 8 envs 1.38 ms per move.  BL_BACKUP_ENVS overrides for tuning.
+    static int tune = -1;
+    if (tune < 0) { const char *e = getenv("BL_BACKUP_ENVS"); tune = e ? atoi(e) : 8; }
+    if (tune > 0 && tune < warps) warps = tune;
     const size_t smem = per_warp * warps;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(backup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
