@@ -62,7 +62,7 @@ __host__ __device__ inline size_t strip_bytes(int W, int K0p) { return (size_t)T
 size_t bias_bytes(int W, int D, int Np) { return ((size_t)(D + 1) * W + Np) * sizeof(float); }
 size_t smem_bytes(int nstages, int A, int W, int D, int Np) {
     return ((size_t)NI * KC * 4 + ACT_CHUNK) * nstages + 2 * (size_t)TILE_M * board_pitch_bytes(A) + 1024 + 2 * TILE_M * sizeof(int32_t) +
-           bias_bytes(W, D, Np);
+           2 * TILE_M * 32 + bias_bytes(W, D, Np);
 }
 
 #define TCK(k) do { if (p.prof) { const long long now_ = clock64(); pc[k] += now_ - tl; tl = now_; } } while (0)
@@ -82,7 +82,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
              *tmem_free = a_ready + 6;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(a_ready + 8);     // keeps sbias 16-byte aligned
     int32_t *tseat0 = reinterpret_cast<int32_t *>(tmem_ptr + 4);  // [2][TILE_M] seat | node << 8 of the tiles' rows
-    float *sbias = reinterpret_cast<float *>(tseat0 + 2 * TILE_M);
+    uint8_t *vmask0 = reinterpret_cast<uint8_t *>(tseat0 + 2 * TILE_M);      // [2][TILE_M][32] legal-move bits of the tiles' rows, 8 cells per byte
+    float *sbias = reinterpret_cast<float *>(vmask0 + 2 * TILE_M * 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (p.B + TILE_M - 1) / TILE_M;
@@ -273,6 +274,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
                 // cell codes: black = {1,3,4}, white = {2,5,6} (hex_core.cuh); channel 0 = the mover's own stones
                 const uint32_t own_mask = seat ? 0x64u : 0x1Au, opp_mask = seat ? 0x1Au : 0x64u;
                 for (int c = hh; c < nk0; c += 2) {
+                    uint32_t vbits8 = 0;
 #pragma unroll
                     for (int g = 0; g < 2; g++) {
                         uint32_t wd[4];
@@ -284,11 +286,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
                                 const int r = cell / S, cc = cell - r * S;
                                 const uint32_t cv = brow[seat ? cc * S + r : cell];
                                 x = ((own_mask >> cv) & 1u) * 0x3C00u | ((opp_mask >> cv) & 1u) * 0x3C000000u;      // fp16 1.0
+                                vbits8 |= (x == 0u ? 1u : 0u) << (g * 4 + u);   // neither side's stone: a legal move (heads.py:101)
                             }
                             wd[u] = x;
                         }
                         *reinterpret_cast<uint4 *>(my_scr + (size_t)c * ACT_CHUNK + g * LBO) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
                     }
+                    if (c < 32) vmask0[((size_t)buf * TILE_M + row) * 32 + c] = (uint8_t)vbits8;   // the heads group reads these
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -417,22 +421,31 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
             const int32_t sv = tseat0[buf * TILE_M + row];
             const bool live = m < p.B && sv >= 0;
             const int seat = live ? (sv & 1) : 0;
-            // legal moves (cell empty) of my row as a bitmask over head columns
-            unsigned long long vm[4] = {0, 0, 0, 0};
-            {
-                int r = 0, c = 0;
-                for (int a = 0; a < A; a++) {
-                    const unsigned long long bit = brow[seat ? c * S + r : a] == BL_EMPTY ? 1ull : 0ull;
-                    vm[a >> 6] |= bit << (a & 63);
-                    if (++c == S) { c = 0; r++; }
-                }
-            }
-            auto vbits = [&](int u) { return (uint32_t)((vm[(u * 16) >> 6] >> ((u * 16) & 63)) & 0xFFFFull); };
-            auto unit = [&](int u, float (&y)[16]) {                // raw head outputs of columns [16u, 16u+16)
-                uint32_t acc[16], acl[16];
-                tmem_ld16(tmem + lane_base + u * 16, acc);
-                if (p.precision == 0) tmem_ld16(tmem + lane_base + LO_COL + u * 16, acl);
+            // legal moves of my row, left by the layer group beside the one-hot operand (8 cells per byte); the value column and
+            // the padding columns read as illegal
+            const uint4 *vrow = reinterpret_cast<const uint4 *>(vmask0 + ((size_t)buf * TILE_M + row) * 32);
+            const uint4 va = vrow[0], vc = vrow[1];
+            auto vbits = [&](int u) {
+                const uint32_t wsel = (u >> 1) == 0 ? va.x : (u >> 1) == 1 ? va.y : (u >> 1) == 2 ? va.z : (u >> 1) == 3 ? va.w
+                                    : (u >> 1) == 4 ? vc.x : (u >> 1) == 5 ? vc.y : (u >> 1) == 6 ? vc.z : vc.w;
+                const uint32_t bits = (u & 1) ? wsel >> 16 : wsel & 0xFFFFu;
+                const int rem = A - u * 16;                        // groups the one-hot stage did not cover hold stale bits
+                return rem >= 16 ? bits : (rem <= 0 ? 0u : bits & ((1u << rem) - 1u));
+            };
+            // raw head outputs of columns [16u, 16u+16) = acc_hh + acc_lo + bias; the NEXT unit's accumulators travel meanwhile
+            uint32_t nxt[16], nxl[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) nxl[j] = 0;
+            auto fetch = [&](int u) {
+                tmem_ld16(tmem + lane_base + u * 16, nxt);
+                if (p.precision == 0) tmem_ld16(tmem + lane_base + LO_COL + u * 16, nxl);
+            };
+            auto unit = [&](int u, float (&y)[16]) {
                 tmem_wait_ld();
+                uint32_t acc[16], acl[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) { acc[j] = nxt[j]; acl[j] = nxl[j]; }
+                fetch(u + 1 < nu ? u + 1 : 0);                     // (wraps to unit 0: the next pass starts there)
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     float d = __uint_as_float(acc[j]);
@@ -440,30 +453,37 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
                     y[j] = d + bh[u * 16 + j];
                 }
             };
+            fetch(0);
             TCK(3);
-            // pass 1: max over the legal actions; the value head's column sits right after the policy's
-            float mx = -BL_INF_F, tanh_v = 0.f;
+            // pass 1: max and sum of exp over the legal actions in ONE sweep (running max, sum rescaled when it moves); the value
+            // head's column sits right after the policy's
+            float mx = -BL_INF_F, sum = 0.f, vraw = 0.f;
             for (int u = 0; u < nu; u++) {
                 float y[16];
                 unit(u, y);
                 const uint32_t vb = vbits(u);
+                float m0 = -BL_INF_F, m1 = -BL_INF_F;
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    if ((vb >> j) & 1u) mx = fmaxf(mx, y[j]);
-                    if (u * 16 + j == A) tanh_v = tanhf(y[j]);
+                for (int j = 0; j < 16; j += 2) {
+                    m0 = fmaxf(m0, ((vb >> j) & 1u) ? y[j] : -BL_INF_F);
+                    m1 = fmaxf(m1, ((vb >> (j + 1)) & 1u) ? y[j + 1] : -BL_INF_F);
+                    if (u * 16 + j == A) vraw = y[j];
+                    if (u * 16 + j + 1 == A) vraw = y[j + 1];
+                }
+                const float mn = fmaxf(mx, fmaxf(m0, m1));
+                if (mn > -BL_INF_F) {                              // (all-illegal so far: nothing to add, and -inf - -inf is NaN)
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        if ((vb >> j) & 1u) s0 += __expf(y[j] - mn);
+                        if ((vb >> (j + 1)) & 1u) s1 += __expf(y[j + 1] - mn);
+                    }
+                    sum = sum * __expf(mx - mn) + (s0 + s1);       // exp(-inf) = 0 on the first legal unit
+                    mx = mn;
                 }
             }
+            const float tanh_v = tanhf(vraw);
             TCK(4);
-            // pass 2: sum of exp
-            float sum = 0.f;
-            for (int u = 0; u < nu; u++) {
-                float y[16];
-                unit(u, y);
-                const uint32_t vb = vbits(u);
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if ((vb >> j) & 1u) sum += __expf(y[j] - mx);
-            }
             const float lse = logf(sum);
             TCK(5);
             // pass 3 — tree mode: logits -> half -> exp table -> pi row + row summary, straight into the search tree (what
@@ -505,6 +525,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
                     }
                 }
             }
+            tmem_wait_ld();                                        // (the wrapped prefetch of the last unit)
             // z is free: the next tile's layer 0 may overwrite it
             tc_fence_before();
             __syncwarp();
