@@ -44,6 +44,7 @@ SIGNATURES = {
     'bl_hex_observe': (c_int, [P, P, P, c_int, c_int, P]),
     'bl_hex_transition': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     'bl_hex_valid': (c_int, [P, P, P, c_int, c_int, P]),
+    'bl_hex_random_transition': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     'bl_mcts_descend': (c_int, [P] * 13 + [c_int] * 4 + [P]),
     'bl_mcts_root': (c_int, [P] * 10 + [c_int] * 4 + [P]),
     'bl_mcts_backup': (c_int, [P] * 7 + [c_int] * 3 + [P]),

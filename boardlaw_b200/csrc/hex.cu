@@ -32,13 +32,14 @@ __device__ __forceinline__ void tile_store(const uint8_t *sb, uint8_t *__restric
 
 // mode bits
 constexpr int F_TRANSITION = 1;   // out-of-place + reset + seat flip + rule check (Hex.step)
+constexpr int F_RANDOM = 2;       // the action is drawn here: the k-th legal move, k = floor(u * n_legal), u a caller-supplied uniform
 
 template <typename StkT, int MODE>
 __global__ void __launch_bounds__(NT) hex_step_kernel(
     const uint8_t *__restrict__ board_in, uint8_t *__restrict__ board_out,
     const int32_t *__restrict__ seats, const void *__restrict__ actions_, float *__restrict__ rewards,
     int32_t *__restrict__ new_seats, uint8_t *__restrict__ terminal, int32_t *__restrict__ error_word,
-    int reset, int B, int S) {
+    int64_t *__restrict__ actions_out, int reset, int B, int S) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int A = S * S;
     uint8_t *sb = smem;                                           // A * PITCH bytes
@@ -54,7 +55,23 @@ __global__ void __launch_bounds__(NT) hex_step_kernel(
     if (tid < nb) {
         const int seat = seats[b];
         long long action;
-        if (MODE & F_TRANSITION) action = reinterpret_cast<const int64_t *>(actions_)[b];
+        if (MODE & F_RANDOM) {
+            // uniformly random legal move (learning.mix, boardlaw/learning.py:6-10 draws Categorical(probs=valid)): count the empty
+            // cells, take the k-th in the mover's frame order (white sees the transpose, hex/__init__.py:154-159)
+            int n_empty = 0;
+            for (int c = 0; c < A; c++) n_empty += sb[c * PITCH + tid] == BL_EMPTY;
+            const float u = reinterpret_cast<const float *>(actions_)[b];
+            int k = (int)__fmul_rn(u, (float)n_empty);
+            k = k < n_empty - 1 ? k : n_empty - 1;
+            k = k > 0 ? k : 0;
+            action = -1;
+            int r = 0, c = 0;
+            for (int a = 0; a < A && action < 0; a++) {
+                if (sb[(seat ? c * S + r : a) * PITCH + tid] == BL_EMPTY && k-- == 0) action = a;
+                if (++c == S) { c = 0; r++; }
+            }
+            actions_out[b] = action;
+        } else if (MODE & F_TRANSITION) action = reinterpret_cast<const int64_t *>(actions_)[b];
         else action = reinterpret_cast<const int32_t *>(actions_)[b];
 
         int win = 0;
@@ -121,7 +138,7 @@ __global__ void __launch_bounds__(256) hex_valid_kernel(
 
 template <typename StkT, int MODE>
 int launch_step(const uint8_t *bin, uint8_t *bout, const int32_t *seats, const void *actions, float *rewards,
-                int32_t *new_seats, uint8_t *terminal, int32_t *error_word, int reset, int B, int S,
+                int32_t *new_seats, uint8_t *terminal, int32_t *error_word, int64_t *actions_out, int reset, int B, int S,
                 cudaStream_t st) {
     const int A = S * S;
     size_t smem = ((A * PITCH + 15) & ~15) + (size_t)A * PITCH * sizeof(StkT);
@@ -131,7 +148,7 @@ int launch_step(const uint8_t *bin, uint8_t *bout, const int32_t *seats, const v
         if (e != cudaSuccess) return (int)e;
     }
     kern<<<(B + NT - 1) / NT, NT, smem, st>>>(bin, bout, seats, actions, rewards, new_seats, terminal,
-                                              error_word, reset, B, S);
+                                              error_word, actions_out, reset, B, S);
     BL_LAUNCH_CHECK();
 }
 
@@ -148,8 +165,8 @@ extern "C" int bl_hex_step(uint8_t *board, const int32_t *seats, const int32_t *
     if (B < 0 || S < 1 || S > 19) return -1;
     if (B == 0) return 0;
     if (S <= 15)
-        return launch_step<uint8_t, 0>(board, board, seats, actions, rewards, nullptr, nullptr, nullptr, 0, B, S, bl_cu(stream));
-    return launch_step<uint16_t, 0>(board, board, seats, actions, rewards, nullptr, nullptr, nullptr, 0, B, S, bl_cu(stream));
+        return launch_step<uint8_t, 0>(board, board, seats, actions, rewards, nullptr, nullptr, nullptr, nullptr, 0, B, S, bl_cu(stream));
+    return launch_step<uint16_t, 0>(board, board, seats, actions, rewards, nullptr, nullptr, nullptr, nullptr, 0, B, S, bl_cu(stream));
 }
 
 extern "C" int bl_hex_transition(const uint8_t *board, const int32_t *seats, const int64_t *actions,
@@ -159,9 +176,21 @@ extern "C" int bl_hex_transition(const uint8_t *board, const int32_t *seats, con
     if (B == 0) return 0;
     if (S <= 15)
         return launch_step<uint8_t, F_TRANSITION>(board, new_board, seats, actions, rewards, new_seats, terminal,
-                                                  error_word, reset, B, S, bl_cu(stream));
+                                                  error_word, nullptr, reset, B, S, bl_cu(stream));
     return launch_step<uint16_t, F_TRANSITION>(board, new_board, seats, actions, rewards, new_seats, terminal,
-                                               error_word, reset, B, S, bl_cu(stream));
+                                               error_word, nullptr, reset, B, S, bl_cu(stream));
+}
+
+extern "C" int bl_hex_random_transition(const uint8_t *board, const int32_t *seats, const float *uniforms,
+                                        uint8_t *new_board, int32_t *new_seats, int64_t *actions, float *rewards,
+                                        uint8_t *terminal, int32_t *error_word, int reset, int B, int S, bl_stream stream) {
+    if (B < 0 || S < 1 || S > 19) return -1;
+    if (B == 0) return 0;
+    if (S <= 15)
+        return launch_step<uint8_t, F_TRANSITION | F_RANDOM>(board, new_board, seats, uniforms, rewards, new_seats, terminal,
+                                                             error_word, actions, reset, B, S, bl_cu(stream));
+    return launch_step<uint16_t, F_TRANSITION | F_RANDOM>(board, new_board, seats, uniforms, rewards, new_seats, terminal,
+                                                          error_word, actions, reset, B, S, bl_cu(stream));
 }
 
 extern "C" int bl_hex_observe(const uint8_t *board, const int32_t *seats, float *obs, int B, int S,

@@ -78,6 +78,21 @@ class Hex(arrdict.namedarrtuple('Hex', fields=('board', 'seats'))):
         return new_world, transition
 
 
+    def step_random(self, uniforms=None, generator=None, reset=True):
+        """One step of a uniformly random playout in one kernel: every env plays a uniformly drawn legal move
+        (``Categorical(probs=worlds.valid.float()).sample()`` + ``worlds.step``, boardlaw/learning.py:8-9).  ``uniforms``
+        (n_envs,) f32 in [0,1) may be injected; otherwise they are drawn on the device.  Returns
+        (new_world, arrdict(terminal, rewards, actions))."""
+        if uniforms is None:
+            uniforms = torch.rand((self.n_envs,), device=self.device, generator=generator)
+        errors = self.board.new_zeros((), dtype=torch.int32)
+        new_board, new_seats, actions, rewards, terminal = cuda.random_transition(
+            self.board.contiguous(), self.seats.int().contiguous(), uniforms.float().contiguous(), reset, errors)
+        new_world = type(self)(board=new_board, seats=new_seats)
+        new_world.errors = errors
+        return new_world, arrdict.arrdict(terminal=terminal, rewards=rewards, actions=actions)
+
+
 def from_string(s, **kwargs):
     """Plays out a position drawn with 'b', 'w', '.' (as boardlaw/hex/tests.py:121-134)."""
     import numpy as np

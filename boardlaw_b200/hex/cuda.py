@@ -65,6 +65,27 @@ def transition(board, seats, actions, reset=True, error_word=None):
     return new_board, new_seats, rewards, terminal
 
 
+def random_transition(board, seats, uniforms, reset=True, error_word=None):
+    """One fused step of a uniformly random playout (the loop body of ``learning.mix``, boardlaw/learning.py:6-10): env b
+    plays its k-th legal move, k = floor(uniforms[b] * n_legal).  Returns (new_board, new_seats, actions, rewards, terminal)."""
+    proxy(board, torch.uint8, 3, 'board'); proxy(seats, torch.int32, 1, 'seats'); proxy(uniforms, torch.float32, 1, 'uniforms')
+    dev = _lib.require_cuda(board, seats, uniforms, error_word)
+    B, S, _ = board.shape
+    if uniforms.shape[0] != B:
+        raise RuntimeError('uniforms must have one entry per env')
+    new_board = torch.empty_like(board)
+    new_seats = torch.empty_like(seats)
+    actions = board.new_empty((B,), dtype=torch.int64)
+    rewards = board.new_empty((B, 2), dtype=torch.float32)
+    terminal = board.new_empty((B,), dtype=torch.bool)
+    if error_word is None:
+        error_word = board.new_zeros((), dtype=torch.int32)
+    check(_lib.lib().bl_hex_random_transition(ptr(board), ptr(seats), ptr(uniforms), ptr(new_board), ptr(new_seats), ptr(actions),
+                                              ptr(rewards), ptr(terminal), ptr(error_word), int(bool(reset)), B, S,
+                                              _lib.stream_for(dev)), 'bl_hex_random_transition')
+    return new_board, new_seats, actions, rewards, terminal
+
+
 # the object planted in ``boardlaw.hex.cuda._cache``
 hexcuda = types.SimpleNamespace(step=step, observe=observe)
 

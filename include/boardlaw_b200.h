@@ -61,6 +61,16 @@ int bl_hex_transition(const uint8_t *board, const int32_t *seats, const int64_t 
                       uint8_t *new_board, int32_t *new_seats, float *rewards, uint8_t *terminal,
                       int32_t *error_word, int reset, int B, int S, bl_stream stream);
 
+/* One step of a uniformly random playout, fused: replaces the loop body of learning.mix
+ * (boardlaw/learning.py:6-10: `Categorical(probs=worlds.valid.float()).sample()` then `worlds.step(actions)`)
+ * and the moves of validation.RandomAgent.  uniforms (B,) f32 in [0,1) are drawn by the caller (the reference draws
+ * inside torch.distributions); env b plays its k-th legal move in the mover's frame order, k = min(floor(u_b * n_legal),
+ * n_legal - 1), which is written to actions (B,) i64; everything else as bl_hex_transition. */
+int bl_hex_random_transition(const uint8_t *board, const int32_t *seats, const float *uniforms,
+                             uint8_t *new_board, int32_t *new_seats, int64_t *actions, float *rewards,
+                             uint8_t *terminal, int32_t *error_word, int reset, int B, int S,
+                             bl_stream stream);
+
 /* valid (B,A) u8 (bool) in the mover's frame = (obs == 0).all(-1) of boardlaw/hex/__init__.py:154-159,
  * computed from the board without materialising obs. */
 int bl_hex_valid(const uint8_t *board, const int32_t *seats, uint8_t *valid, int B, int S,

@@ -119,6 +119,22 @@ class HexWorld:
         return HexWorld(self.board[idx], self.seats[idx], self.ops)
 
 
+def random_actions(valid, uniforms):
+    """The draw of bl_hex_random_transition restated: env b takes its k-th legal move (mover's frame order),
+    k = min(floor(fp32(u_b) * fp32(n_legal)), n_legal - 1) — a uniform draw over the legal moves, i.e. the distribution of
+    ``Categorical(probs=worlds.valid.float()).sample()`` (boardlaw/learning.py:8)."""
+    import numpy as np
+    v = valid.numpy().astype(bool)
+    u = uniforms.numpy().astype(np.float32)
+    n = v.sum(-1)
+    k = np.minimum((u * n.astype(np.float32)).astype(np.int64), n - 1)
+    k = np.maximum(k, 0)
+    order = np.cumsum(v, -1) - 1                                   # rank of each legal move
+    hit = v & (order == k[:, None])
+    actions = np.where(hit.any(-1), hit.argmax(-1), -1)
+    return torch.from_numpy(actions.astype(np.int64))
+
+
 def random_playout(world, n_steps):
     """``learning.mix``-style decorrelation (boardlaw/learning.py:6-10): uniformly random valid moves."""
     for _ in range(n_steps):
