@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
     for (int w = 0; w < NW; w++) cm[w] = 0;
     // optional phase clock (bl_debug_set_phase_profile): cycles per phase summed over warps, for DESIGN.md's latency budget
     long long pc[PROF ? 13 : 1], tlast = PROF ? clock64() : 0;
+    unsigned n_service = 0, n_pass = 0;               // PROF: trips with the service block / with a pass (slots 13, 14)
 #pragma unroll
     for (int k = 0; k < (PROF ? 13 : 1); k++) pc[k] = 0;
 #define tick(k) do { if (PROF) { __syncwarp(__activemask()); const long long now_ = clock64(); pc[k] += now_ - tlast; tlast = now_; } } while (0)
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
         tick(0);
         const unsigned needm = livem & ~passm;
         if (passm == 0 || __popc(needm) * gate_den >= __popc(livem) * gate_num) {
+            if (PROF) n_service++;
             // ---- G: inverse-CDF search over the running sums (descend_kernel, cuda.cu:160-176) ----------------------------------
             if (state == ST_SAMPLE) {
                 // every term is >= 0 (checked for child terms in C), so the sums are non-decreasing: first index with sum >= r.
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
         const bool pass = state == ST_PASS || state == ST_FINAL;
         float accS = 0.f, accG = 0.f;
         if (__any_sync(FULL, pass)) {
+            if (PROF) n_pass++;
             const float bS = alpha, bG = __fmul_rn(alpha, alpha);
             const float yS = bl_rcp_fast(bS), yG = -bl_rcp_fast(bG); // g terms: divide lambda*pi by -(alpha^2); alpha in [1e-4, ~c_puct+1]
             const u64 yS2 = pk(yS, yS), yG2 = pk(yG, yG), nbS2 = pk(-bS, -bS), bG2 = pk(bG, bG);
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, cons
             for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
             if (lane == 0) atomicAdd(prof + k, (unsigned long long)m);
         }
-        if (lane == 0) atomicAdd(prof + 15, 1ull);
+        if (lane == 0) { atomicAdd(prof + 15, 1ull); atomicAdd(prof + 13, (unsigned long long)n_service); atomicAdd(prof + 14, (unsigned long long)n_pass); }
     }
     bl_count(t.counters, C_EVALS, c_evals);
     bl_count(t.counters, C_CHILDREN, c_children);

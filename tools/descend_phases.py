@@ -41,6 +41,7 @@ for label, prof_on in (('plain', False), ('clocked', True)):
         print(f'warps x launches = {nw}; avg cycles per warp per launch = {tot / nw:.0f}')
         for k, n in enumerate(names):
             print(f'  {n:16s} {c[k] / nw:9.0f} cycles  {100 * c[k] / tot:5.1f}%')
+        print(f'  trips per warp per launch: {c[13] / nw:.1f} with the service block, {c[14] / nw:.1f} with a pass')
         ncta = max(c[31], 1)
         print(f'network kernel: CTAs x launches = {ncta}')
         for k, n in ((16, 'mma: wait operand'), (17, 'mma: wait weights'), (18, 'mma: issue'), (20, 'epi: board staging'), (21, 'epi: one-hot operand'),
