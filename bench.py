@@ -102,7 +102,7 @@ def algorithmic_bytes(S, T, counters, n_desc):
 
 def ncu_traffic(kind):
     """dram read + write bytes per launch of the dominant kernel, from the committed ``ncu --set full`` summary (profiles/)."""
-    name = {'descend_expand': 'r01_descend_v3_ncu_full.txt', 'net': 'r01_fc_tc_ncu_full.txt'}.get(kind)
+    name = {'descend_expand': 'r01_descend_v3c_ncu_full.txt', 'net': 'r01_fc_tc_v2_ncu_full.txt', 'backup': 'r01_backup_v2_ncu_full.txt'}.get(kind)
     f = ROOT / 'profiles' / name if name else None
     if not f or not f.exists():
         return None
