@@ -58,7 +58,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            self.rows.append([x.strip() for x in line.split(',')] + [time.time()])
+
+    def window(self, t0, t1):
+        """Keeps the samples taken inside the timed region [t0, t1]; a region shorter than nvidia-smi's period keeps the samples
+        nearest to it instead (taken under the same load: the sampler runs from the warm-up on)."""
+        inside = [r for r in self.rows if t0 <= r[-1] <= t1]
+        self.in_window = bool(inside)
+        if not inside:
+            inside = sorted(self.rows, key=lambda r: min(abs(r[-1] - t0), abs(r[-1] - t1)))[:3]
+        self.rows = inside
 
     def __exit__(self, *a):
         if self.proc:
@@ -71,7 +80,10 @@ class ClockSampler:
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == 'Active' for r in self.rows)]
         smax = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax, 'reasons': reasons, 'samples': len(sm)}
+        out = {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax, 'reasons': reasons, 'samples': len(sm)}
+        if not getattr(self, 'in_window', True):
+            out['note'] = 'timed region shorter than the sampling period: nearest samples under the same load (warm-up / e2e pass)'
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -189,6 +201,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    clocks.__enter__()                                         # nvidia-smi takes a while to start: it runs from the warm-up on
     for _ in range(max(args.warmup, 3)):
         play.step()
     eng = engine_for(play.worlds, T)
@@ -197,14 +211,17 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = eng.launches
-    with ClockSampler(local) as clocks:
-        e0.record()
-        for _ in range(args.steps):
-            play.step()
-        if pool is not None:
-            pool.wait()
-        e1.record()
-        barrier()
+    t_begin = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        play.step()
+    if pool is not None:
+        pool.wait()
+    e1.record()
+    barrier()
+    t_end = time.time()
+    clocks.__exit__()
+    clocks.window(t_begin, t_end)
     ms = e0.elapsed_time(e1)
     gpu_launches = eng.launches - launches0 + args.steps      # + the env transition kernel of worlds.step
     if world > 1:
