@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(XNT) expand_step_kernel(bl_tree t, int sim) {
 #endif
 
 template <int NCH, bool PROF>
-__global__ void __launch_bounds__(32) descend_v3_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_t seed,
+__global__ void __launch_bounds__(32, 7) descend_v3_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_t seed,
                                                         ChildEntry *__restrict__ clists, int cap, unsigned long long *prof,
                                                         int gate_num, int gate_den, int fuse_expand) {
     constexpr int PS = 4 * NCH;                         // row pitch in floats; NCH odd => conflict-free 128-bit lane-private rows
