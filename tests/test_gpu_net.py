@@ -76,3 +76,30 @@ def test_forward_through_world_api():
     assert torch.equal(d.v[:, 0], -d.v[:, 1])
     e = net(Hex.initial(0, S, device='cuda'))
     assert e.logits.shape == (0, 25)
+
+
+@pytest.mark.parametrize('S,W,D,B', [(9, 256, 4, 1000), (11, 512, 8, 700), (5, 32, 2, 300)])
+def test_forward_amp_mode(S, W, D, B):
+    """precision='amp' (fp16 operands, fp32 accumulation — the precision class of the reference's autocast in
+    MCTS.simulate, boardlaw/mcts/__init__.py:131-133): one tensor-core product per K-step instead of three.  Within
+    half-precision operand error of the fp32 reference, same legal-move mask, and not bit-identical to the fp32 mode."""
+    from boardlaw_b200 import heads
+    from boardlaw_b200.networks import FCModel
+    from oracle import pyref
+    sd = pyref.synth_state_dict(S, W, D, seed=S + W)
+    w = gu.start_position(S, B, S * S // 2, seed=W)
+    ref = pyref.FCNet(sd)(w)
+    outs = {}
+    for precision in ('fp32', 'amp'):
+        net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(S * S), width=W, depth=D, precision=precision)
+        net.load_state_dict(sd)
+        logits, v = net.cuda().evaluate(w.board.cuda(), w.seats.cuda())
+        torch.cuda.synchronize()
+        outs[precision] = (logits.cpu(), v.cpu())
+    finite = torch.isfinite(ref.logits)
+    assert torch.equal(torch.isfinite(outs['amp'][0]), finite)
+    err = (outs['amp'][0][finite] - ref.logits[finite]).abs().max().item()
+    errv = (outs['amp'][1] - ref.v).abs().max().item()
+    print(f'S{S} W{W} D{D} amp: max |dlogit| {err:.2e}, max |dv| {errv:.2e}')
+    assert err < 3e-2 and errv < 3e-2
+    assert not torch.equal(outs['amp'][0], outs['fp32'][0])
