@@ -1,0 +1,431 @@
+// Tree descent with FOUR lanes per env for sm_100a — the hot loop of MCTS.simulate (descend_kernel + policy + newton_search,
+// boardlaw/mcts/cpp/cuda.cu:35-99,138-182), same arithmetic as descend.cu (one lane per env), different mapping.
+//
+// Why: with one lane per env the number of warps is B/32 (c2: 1 024 warps = 1.7 per SM sub-partition) and the kernel runs at
+// the LATENCY of its own dependent chains (issue-active 33 %).  The only part of a Newton pass that is
+// inherently serial is the pair of fp32 running sums (the reference adds the A terms left to right); the terms themselves —
+// two correctly rounded divisions per action — are independent.  So an env gets a group of four lanes:
+//
+//   * term phase: each lane computes the S and g terms of every fourth 4-action chunk from its register-resident slice of
+//     the lambda*pi row (packed FMUL2/FFMA2 Markstein division by the shared divisors alpha and alpha^2) and parks them in
+//     the env's two shared-memory rows;
+//   * child terms (actions that have a child: full divisions) are patched into the rows by the lane that owns the child;
+//   * chain phase: lane 0 of the group runs the S chain and lane 1 the g chain over the rows (one 128-bit load, four
+//     dependent additions and — for S — one 128-bit store of the running sums per chunk); the running sums are the sampling
+//     loop's `total`;
+//   * services (sample / advance / visit) are split over the four lanes as well: the inverse-CDF count is a four-way
+//     partial count, a child's record is fetched and adopted by the lane (child id & 3), reductions are group shuffles.
+//
+// This gives 4x the warps (c2: 4 096 = 28 per SM, 7 per sub-partition) at a quarter of the registers per lane (the row slice is
+// 2*ceil(NCH/4) register pairs), so the chains of different envs overlap in the issue slots the one-lane kernel leaves idle.
+// Every fp32 operation, its operands and its order are those of descend.cu (and of the oracle); only who executes it differs.
+//
+// Compiled with -fmad=false -prec-div=true -ftz=false (see build.py); fused operations are explicit.
+#include <cstdio>
+#include <cstdlib>
+
+#include "descend_common.cuh"
+
+namespace {
+
+template <int NCH>
+struct MwCfg {
+    static constexpr int PS = 4 * NCH;                 // floats per row; NCH odd => the group's 128-bit accesses hit distinct banks
+    static constexpr int CPL = (NCH + 3) / 4;          // chunks per lane
+    static constexpr int KS = NCH;                     // child entries per env held in shared memory; the rest go to global scratch
+    static constexpr int ENVS = 32;                    // envs per CTA: 4 warps x 8 groups
+    static constexpr int SMEM = ENVS * (2 * PS * 4 + 16 * KS);
+    static constexpr int FIT = 233472 / (SMEM + 1024);
+    static constexpr int MINB = FIT > 7 ? 7 : (FIT < 1 ? 1 : FIT);
+};
+
+__device__ __forceinline__ void cp16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(128, MwCfg<NCH>::MINB)
+descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_t seed, ChildEntry *__restrict__ clists, int cap,
+                  int gate_num, int gate_den, int fuse_expand) {
+    using C = MwCfg<NCH>;
+    constexpr int PS = C::PS, CPL = C::CPL, KS = C::KS;
+    constexpr int MW = 4;                              // 64-bit words of the children-of-this-node mask (T <= 256; else list walk)
+    extern __shared__ float4 smem4[];
+    const int A = t.A, T = t.T;
+    const int lane = threadIdx.x & 31, sub = lane & 3, gl = lane & ~3;
+    const unsigned gmask = 0xFu << gl;                 // the env's four lanes
+    const int slot = (threadIdx.x >> 5) * 8 + (lane >> 2);
+    // per env: [S terms in / running S sums out | g terms]; rows of one env are adjacent so that the chain lanes' accesses
+    // (lane 0: S row, lane 1: g row, of two envs per quarter-warp) fall into four different bank quartets
+    float *ps = reinterpret_cast<float *>(smem4) + slot * (2 * PS);
+    float *pg = ps + PS;
+    float4 *ps4 = reinterpret_cast<float4 *>(ps), *pg4 = reinterpret_cast<float4 *>(pg);
+    float4 *pe4 = smem4 + (C::ENVS * 2 * PS) / 4 + slot * KS;   // child entries {q, top, action | id << 8, flags}; raw records in flight
+    const uint32_t ps_addr = smem_u32(ps), pg_addr = smem_u32(pg), pe_addr = smem_u32(pe4);
+    const bl_qnorm qn(t.qrange + 2 * sim);
+    const int nrow4 = t.AP >> 2;
+    const int KW = (T + 63) >> 6;
+    const bool scan_ok = T <= 64 * MW;
+
+    int b = (int)blockIdx.x * C::ENVS + slot;
+    if (b >= t.B) b = -1;
+    ChildEntry *cl = clists + (size_t)(b < 0 ? 0 : b) * cap;
+
+    u64 tp[2 * CPL];                                  // this lane's slice of lambda*pi: chunks sub, sub+4, ... as element pairs
+    int cur = 0, parent = 0, action = -1, state = ST_IDLE, nc = 0, nown = 0, it = 0, cur_seat = 0;
+    int res_leaf = -1, res_parent = 0, res_action = -1;
+    float alpha = 1.f, error = 0.f, r = 0.f, c_puct = 0.f;
+    uint32_t nzpos = 0;
+    unsigned c_evals = 0, c_children = 0, c_iters = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * CPL; k++) tp[k] = 0;
+
+    // child entry j of this lane lives in slot 4*j + sub (so a slot's owner is slot & 3)
+    auto get = [&](int i) {
+        ChildEntry e;
+        if (i < KS) {
+            const float4 v = pe4[i];
+            e.q = v.x; e.top = v.y;
+            const uint32_t u = __float_as_uint(v.z);
+            e.a = u & 255; e.id = u >> 8; e.flags = __float_as_int(v.w);
+        } else e = cl[i];
+        return e;
+    };
+    auto put = [&](int i, const ChildEntry &e) {
+        if (i < KS) pe4[i] = make_float4(e.q, e.top, __uint_as_float((uint32_t)e.a | ((uint32_t)e.id << 8)), __int_as_float(e.flags));
+        else cl[i] = e;
+    };
+    // asynchronous fetch of what a visit of node n needs at a known address: row summary -> pg[0..3], children mask ->
+    // pg[4..], pi row -> the (dead) S row; consumed at the next service
+    auto prefetch_node = [&](int n) {
+        const size_t s = (size_t)b * T + n;
+        if (sub == 0) cp16(pg_addr, t.aux + s);
+        if (sub == 1 && scan_ok)
+            for (int w = 0; w < KW; w++) cp8(pg_addr + 16u + 8u * w, t.kids + s * KW + w);
+        const float4 *row = reinterpret_cast<const float4 *>(t.pi + s * t.AP);
+#pragma unroll
+        for (int k = 0; k < CPL; k++) {
+            const int c = 4 * k + sub;
+            if (c < NCH && c < nrow4) cp16(ps_addr + 16u * c, row + c);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (b >= 0) {
+        const bl_node root = bl_ld_node(t.node + (size_t)b * T);
+        c_puct = bl_h2f(t.c_puct[b]);
+        cur_seat = root.seat;
+        if (root.terminal) state = ST_DONE;           // a terminal root ends the descent at the first service (leaf = 0, no action)
+        else { state = ST_VISIT; prefetch_node(0); }
+    }
+
+    while (true) {
+        const bool pass0 = state == ST_PASS || state == ST_FINAL;
+        const unsigned livem = __ballot_sync(FULL, state != ST_IDLE), passm = __ballot_sync(FULL, pass0);
+        if (livem == 0) break;
+        const unsigned needm = livem & ~passm;
+        if (passm == 0 || __popc(needm) * gate_den >= __popc(livem) * gate_num) {
+            // ---- sample: l = #{a < A : sum[a] < r} over the running sums (descend_kernel, cuda.cu:160-176; see descend.cu) ----
+            if (state == ST_SAMPLE) {
+                int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < CPL; k++) {
+                    const int c = 4 * k + sub;
+                    if (c < NCH && c < nrow4) {
+                        const float4 v = ps4[c];
+                        const int a0 = 4 * c;
+                        cnt += (a0 < A && v.x < r) + (a0 + 1 < A && v.y < r) + (a0 + 2 < A && v.z < r) + (a0 + 3 < A && v.w < r);
+                    }
+                }
+                cnt += __shfl_xor_sync(gmask, cnt, 1);
+                cnt += __shfl_xor_sync(gmask, cnt, 2);
+                const int l = cnt, first_nz = nzpos & 255, last_nz = (nzpos >> 8) & 255;
+                action = first_nz == 255 ? -1 : (l < A ? (r <= 0.f ? first_nz : l) : last_nz);
+                state = ST_ADVANCE;
+            }
+            // ---- advance: step to the chosen child; its row starts travelling ----
+            if (state == ST_ADVANCE) {
+                parent = cur;
+                unsigned found = 0;
+                for (int j = 0; j < nown; j++) {
+                    const ChildEntry e = get(4 * j + sub);
+                    if (e.a == action) found = 0x80000000u | ((unsigned)e.id << 16) | ((unsigned)e.flags & 0xffffu);
+                }
+                found |= __shfl_xor_sync(gmask, found, 1);
+                found |= __shfl_xor_sync(gmask, found, 2);
+                const int next = (found >> 31) ? (int)((found >> 16) & 0x7fffu) : -1, nflags = (int)(found & 0xffffu);
+                cur = action >= 0 ? next : -1;
+                if (cur >= 0 && !(nflags >> 8)) { cur_seat = nflags & 255; state = ST_VISIT; prefetch_node(cur); }
+                else state = ST_DONE;                               // new leaf, existing terminal child, or no legal action
+            }
+            // ---- done: the descent's result (existing terminal child or -1: the expand step decides) ----
+            if (state == ST_DONE) {
+                if (sub == 0) {
+                    t.leaf[b] = (int16_t)cur;
+                    t.leaf_parent[b] = (int16_t)parent;
+                    t.leaf_action[b] = (int16_t)action;
+                }
+                res_leaf = cur; res_parent = parent; res_action = action;
+                state = ST_IDLE;
+            }
+            // ---- visit: children, N, lambda, random number, row slice into registers ----
+            const bool visit = state == ST_VISIT;
+            if (visit) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();                                           // the group's copies have landed for all four lanes
+            if (visit) {
+                const size_t node0 = (size_t)b * T;
+                const int seat = cur_seat;
+                if (rands) r = bl_h2f(rands[node0 + cur]);
+                else r = bl_uniform_half_grid(bl_philox(seed ^ (t.counters[C_MOVE] * 0x9E3779B97F4A7C15ull), (uint64_t)b,
+                                                        ((uint64_t)sim << 32) | (uint32_t)cur).x);
+                bl_aux ax;
+                { union { float4 f; bl_aux a; } x; x.f = pg4[0]; ax = x.a; }
+                int N = 0;
+                nown = 0;
+                auto adopt = [&](const bl_node &ch, int id) {
+                    put(4 * nown + sub, ChildEntry{qn.fast(seat ? ch.w[1] : ch.w[0], ch.n), 0.f, (int)ch.relation, id,
+                                                   (int)ch.seat | ((int)ch.terminal << 8)});
+                    N += ch.n;
+                    nown++;
+                };
+                if (scan_ok) {
+                    // this lane's children = the mask bits whose node id is sub mod 4; their records are fetched together
+                    // straight into the lane's entry slots, then adopted in place
+                    u64 mm[MW];
+#pragma unroll
+                    for (int w = 0; w < MW; w++)
+                        mm[w] = w < KW ? *reinterpret_cast<const u64 *>(pg + 4 + 2 * w) & (0x1111111111111111ull << sub) : 0ull;
+                    int j = 0;
+#pragma unroll
+                    for (int w = 0; w < MW; w++)
+                        for (u64 m = mm[w]; m; m &= m - 1) {
+                            const int id = w * 64 + __ffsll((long long)m) - 1, s = 4 * j + sub;
+                            if (s < KS) cp16(pe_addr + 16u * s, t.node + node0 + id);
+                            j++;
+                        }
+                    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                    for (int w = 0; w < MW; w++)
+                        for (u64 m = mm[w]; m; m &= m - 1) {
+                            const int id = w * 64 + __ffsll((long long)m) - 1, s = 4 * nown + sub;
+                            bl_node ch;
+                            if (s < KS) { union { float4 f; bl_node n; } x; x.f = pe4[s]; ch = x.n; }
+                            else ch = bl_ld_node(t.node + node0 + id);
+                            adopt(ch, id);
+                        }
+                } else {
+                    const bl_node nd = bl_ld_node(t.node + node0 + cur);
+                    for (int c = nd.first_child; c >= 0;) {
+                        const bl_node ch = bl_ld_node(t.node + node0 + c);
+                        if ((c & 3) == sub) adopt(ch, c);
+                        c = ch.next_sib;
+                    }
+                }
+                N += __shfl_xor_sync(gmask, N, 1);
+                N += __shfl_xor_sync(gmask, N, 2);
+                nc = nown + __shfl_xor_sync(gmask, nown, 1);
+                nc += __shfl_xor_sync(gmask, nc, 2);
+                N += A - nc;                                        // every child-less action counts 1 (cuda.cu:91)
+                const float lambda = bl_lambda(c_puct, N, A);
+                nzpos = (uint32_t)ax.first_nz | ((uint32_t)ax.last_nz << 8);
+                // alpha seed (newton_search, cuda.cu:44-50): max_a (q[a] + max(lambda*pi[a], 1e-4)); the child-less part is
+                // max(RN(lambda*max_pi), 1e-4) (rounding is monotone); max is exact, so the group reduction is order-free
+                float alpha0 = fmaxf(__fmul_rn(lambda, ax.max_pi), 1.e-4f);
+                for (int j = 0; j < nown; j++) {
+                    ChildEntry e = get(4 * j + sub);
+                    e.top = __fmul_rn(lambda, ps[e.a]);             // the landed row still holds pi
+                    alpha0 = fmaxf(alpha0, __fadd_rn(e.q, fmaxf(e.top, 1.e-4f)));
+                    put(4 * j + sub, e);
+                }
+                alpha0 = fmaxf(alpha0, __shfl_xor_sync(gmask, alpha0, 1));
+                alpha0 = fmaxf(alpha0, __shfl_xor_sync(gmask, alpha0, 2));
+                const u64 lam2 = pk(lambda, lambda);
+#pragma unroll
+                for (int k = 0; k < CPL; k++) {                   // top = lambda*pi, this lane's chunks of the landed row
+                    const int c = 4 * k + sub;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < NCH && c < nrow4) v = ps4[c];
+                    tp[2 * k] = mul2(pk(v.x, v.y), lam2); tp[2 * k + 1] = mul2(pk(v.z, v.w), lam2);
+                }
+                const bool tiny = __fmul_rn(lambda, bl_minnz(ax)) < BL_TINY;
+                alpha = alpha0; it = 0; error = BL_INF;
+                state = tiny ? ST_SLOW : ST_PASS;
+                if (sub == 0) { c_evals++; c_children += nc; }
+            }
+            __syncwarp();                                           // every read of the landed rows precedes the term phase's writes
+        }
+
+        // ---- terms of this pass: child-less form for every action, then the child terms patched over them ----
+        bool pass = state == ST_PASS || state == ST_FINAL;
+        if (__any_sync(FULL, pass)) {
+            if (pass) {
+                const float bS = alpha, bG = __fmul_rn(alpha, alpha);
+                const float yS = bl_rcp_fast(bS), yG = -bl_rcp_fast(bG);   // g terms: divide lambda*pi by -(alpha^2)
+                const u64 yS2 = pk(yS, yS), yG2 = pk(yG, yG), nbS2 = pk(-bS, -bS), bG2 = pk(bG, bG);
+#pragma unroll
+                for (int k = 0; k < CPL; k++) {
+                    const int c = 4 * k + sub;
+                    if (c < NCH && c < nrow4) {
+                        const u64 t01 = tp[2 * k], t23 = tp[2 * k + 1];
+                        u64 q = mul2(t01, yS2), rr = fma2(nbS2, q, t01);
+                        const u64 s01 = fma2(rr, yS2, q);
+                        q = mul2(t01, yG2); rr = fma2(bG2, q, t01);
+                        const u64 h01 = fma2(rr, yG2, q);
+                        q = mul2(t23, yS2); rr = fma2(nbS2, q, t23);
+                        const u64 s23 = fma2(rr, yS2, q);
+                        q = mul2(t23, yG2); rr = fma2(bG2, q, t23);
+                        const u64 h23 = fma2(rr, yG2, q);
+                        ps4[c] = make_float4(lo(s01), hi(s01), lo(s23), hi(s23));
+                        pg4[c] = make_float4(lo(h01), hi(h01), lo(h23), hi(h23));
+                    }
+                }
+            }
+            __syncwarp();
+            bool bad = false;
+            if (pass)
+                for (int j = 0; j < nown; j++) {
+                    const ChildEntry e = get(4 * j + sub);
+                    const float bot = __fsub_rn(alpha, e.q), bb = __fmul_rn(bot, bot);
+                    const float sv = bl_div_fast(e.top, bot), gv = bl_div_fast(-e.top, bb);
+                    ps[e.a] = sv;
+                    pg[e.a] = gv;
+                    // bot outside [2^-60, 2^60] leaves the branch-free division's safe range; a negative / non-finite term would
+                    // break the monotone running sums: both go to the exact serial path
+                    bad |= !(bot >= 8.67e-19f && bot <= 1.15e18f) || !(sv >= 0.f && sv <= 3.0e38f);
+                }
+            const unsigned badm = __ballot_sync(FULL, bad);
+            if (pass && (badm & gmask)) state = ST_SLOW;
+            __syncwarp();
+        }
+        // ---- exact serial fallback: the reference loops verbatim, run redundantly by the group's four lanes ----
+        const bool slow = state == ST_SLOW;
+        if (__any_sync(FULL, slow)) {
+            if (slow) {
+#pragma unroll
+                for (int k = 0; k < CPL; k++) {
+                    const int c = 4 * k + sub;
+                    if (c < NCH) ps4[c] = make_float4(lo(tp[2 * k]), hi(tp[2 * k]), lo(tp[2 * k + 1]), hi(tp[2 * k + 1]));
+                }
+            }
+            __syncwarp();
+            if (slow) {
+                auto topf = [&](int a) { return ps[a]; };
+                auto qf = [&](int a) {
+                    float q = 0.f;
+                    for (int s = 0; s < 4; s++) {
+                        const int n_s = __shfl_sync(gmask, nown, gl + s);
+                        for (int j = 0; j < n_s; j++) { const ChildEntry e = get(4 * j + s); if (e.a == a) q = e.q; }
+                    }
+                    return q;
+                };
+                int iters;
+                const float al = bl_newton_f(topf, qf, A, &iters);
+                action = bl_sample_f(topf, qf, A, al, r);
+                if (sub == 0) c_iters += iters;
+                state = ST_ADVANCE;
+            }
+            __syncwarp();
+        }
+
+        // ---- one Newton pass: the two sequential sums, S on the group's lane 0 and g on lane 1 ----
+        pass = state == ST_PASS || state == ST_FINAL;
+        if (__any_sync(FULL, pass)) {
+            float acc = 0.f;
+            if (pass && sub < 2) {
+                float4 *row = sub ? pg4 : ps4;
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    if (c < nrow4) {
+                        const float4 v = row[c];
+                        acc = __fadd_rn(acc, v.x); const float o0 = acc;
+                        acc = __fadd_rn(acc, v.y); const float o1 = acc;
+                        acc = __fadd_rn(acc, v.z); const float o2 = acc;
+                        acc = __fadd_rn(acc, v.w); const float o3 = acc;
+                        if (sub == 0) row[c] = make_float4(o0, o1, o2, o3);
+                    }
+                }
+            }
+            __syncwarp();
+            const float accS = __shfl_sync(FULL, acc, gl), accG = __shfl_sync(FULL, acc, gl | 1);
+            // ---- Newton update (newton_search, cuda.cu:57-66) ----
+            if (pass) {
+                if (state == ST_PASS) {
+                    it++;
+                    if (sub == 0) c_iters++;
+                    const float ne = __fsub_rn(accS, 1.f);
+                    if ((ne < 1e-3f) || (error == ne)) state = ST_SAMPLE;
+                    else {
+                        alpha = __fsub_rn(alpha, __fdiv_rn(ne, accG));
+                        error = ne;
+                        if (it == 100) state = ST_FINAL;            // loop bound hit: one more pass with the last alpha, no test
+                    }
+                } else {
+                    state = ST_SAMPLE;
+                }
+            }
+        }
+    }
+    // ---- expand + env step of the group's env on its lane 0, in the env's (now dead) rows ----
+    if (fuse_expand && b >= 0 && sub == 0)
+        bl_expand_one(t, sim, b, res_leaf, res_parent, res_action, reinterpret_cast<uint32_t *>(ps), reinterpret_cast<uint8_t *>(pg));
+    bl_count(t.counters, C_EVALS, c_evals);
+    bl_count(t.counters, C_CHILDREN, c_children);
+    bl_count(t.counters, C_ITERS, c_iters);
+    bl_count(t.counters, C_DESCENTS, (b >= 0 && sub == 0) ? 1u : 0u);
+}
+
+int g_mw_gate_num = 1, g_mw_gate_den = 2, g_mw_fuse = 1;
+void read_mw_env() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (const char *e = getenv("BL_MW_GATE")) {
+        int a = 0, b = 0;
+        if (sscanf(e, "%d/%d", &a, &b) == 2 && a >= 0 && b > 0) { g_mw_gate_num = a; g_mw_gate_den = b; }
+    }
+    if (const char *e = getenv("BL_MW_FUSE")) g_mw_fuse = atoi(e);
+}
+
+template <int NCH>
+int launch_mw(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st) {
+    using C = MwCfg<NCH>;
+    static bool ready = false;
+    if (!ready) {
+        if (C::SMEM > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(descend_mw_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+            if (e != cudaSuccess) return (int)e;
+        }
+        ready = true;
+    }
+    const int cap = bl_mw_child_cap(t);
+    const int64_t envs = ((int64_t)t->B + 31) / 32 * 32;
+    if (envs * cap * (int64_t)sizeof(ChildEntry) > t->scratch_bytes) return -3;
+    const bool fused = g_mw_fuse && t->BP <= 16 * NCH;               // the env's rows hold a board + flood-fill stack
+    descend_mw_kernel<NCH><<<(unsigned)(envs / 32), 128, C::SMEM, st>>>(*t, sim, rands, seed, reinterpret_cast<ChildEntry *>(t->scratch), cap,
+                                                                       g_mw_gate_num, g_mw_gate_den, fused ? 1 : 0);
+    if (cudaError_t e = cudaGetLastError()) return (int)e;
+    return fused ? 0 : bl_expand_step(t, sim, st);
+}
+
+}  // namespace
+
+int bl_mw_child_cap(const bl_tree *t) { return (t->T + 3) & ~3; }
+int64_t bl_mw_scratch_bytes(const bl_tree *t) {
+    return (((int64_t)t->B + 31) / 32 * 32) * bl_mw_child_cap(t) * (int64_t)sizeof(ChildEntry);
+}
+
+int bl_descend_mw(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st) {
+    read_mw_env();
+    if (t->A > 255) return -2;                                      // entries pack the action into 8 bits
+    const int nch = (t->A + 3) / 4;
+    if (nch <= 3) return launch_mw<3>(t, sim, rands, seed, st);
+    if (nch <= 7) return launch_mw<7>(t, sim, rands, seed, st);
+    if (nch <= 13) return launch_mw<13>(t, sim, rands, seed, st);
+    if (nch <= 21) return launch_mw<21>(t, sim, rands, seed, st);
+    if (nch <= 31) return launch_mw<31>(t, sim, rands, seed, st);
+    if (nch <= 43) return launch_mw<43>(t, sim, rands, seed, st);
+    return -2;
+}

@@ -396,7 +396,16 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (sim < 1 || sim >= t->T) return -1;
-    if (g_descend_variant == 2) return bl_descend_v3(t, sim, rands, seed, bl_cu(stream));
+    static bool env_read = false;
+    if (!env_read) {                                          // BL_DESCEND_VARIANT=1|2|3 overrides the default for tuning runs
+        env_read = true;
+        if (const char *e = getenv("BL_DESCEND_VARIANT")) { const int v = atoi(e); if (v >= 1 && v <= 3) g_descend_variant = v; }
+    }
+    if (g_descend_variant == 3) {
+        const int rc = bl_descend_mw(t, sim, rands, seed, bl_cu(stream));
+        if (rc != -2 && rc != -3) return rc;                 // unsupported shape / scratch: the one-lane kernel takes it
+    }
+    if (g_descend_variant >= 2) return bl_descend_v3(t, sim, rands, seed, bl_cu(stream));
     size_t smem = descend_smem(t->A);
     if (smem > 227 * 1024) return -2;
     if (smem > 48 * 1024) {
@@ -409,7 +418,7 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
 }
 
 extern "C" int bl_debug_set_descend_variant(int variant) {
-    if (variant != 1 && variant != 2) return -1;
+    if (variant < 1 || variant > 3) return -1;
     g_descend_variant = variant;
     return 0;
 }

@@ -57,6 +57,10 @@ __device__ __forceinline__ float bl_minnz(const bl_aux &a) { return __uint_as_fl
 // descend.cu: task-parallel descent (writes t.leaf = existing terminal child or -1, t.leaf_parent, t.leaf_action)
 // followed by expand + env step.  Returns a cudaError_t / negative argument error.
 int bl_descend_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
+// descend_mw.cu: the same descent with four lanes per env (4x the warps); -3 = scratch too small, -2 = unsupported
+int bl_descend_mw(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
+int bl_mw_child_cap(const bl_tree *t);
+int64_t bl_mw_scratch_bytes(const bl_tree *t);
 // descend.cu: expand + env step of the descents recorded in t.leaf / leaf_parent / leaf_action
 int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st);
 // descend.cu: device buffer of the optional phase clock (NULL = off); slots 0..15 descent, 16..31 network
