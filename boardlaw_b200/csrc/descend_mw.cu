@@ -28,13 +28,14 @@
 
 namespace {
 
-template <int NCH>
+template <int NCH, int L>
 struct MwCfg {
-    static constexpr int PS = 4 * NCH;                 // floats per row; NCH odd => the group's 128-bit accesses hit distinct banks
-    static constexpr int CPL = (NCH + 3) / 4;          // chunks per lane
+    static constexpr int PS = 4 * NCH;                 // floats per row; NCH odd => eight consecutive rows start in eight different bank quartets
+    static constexpr int CPL = (NCH + L - 1) / L;      // chunks per lane
     static constexpr int KS = NCH;                     // child entries per env held in shared memory; the rest go to global scratch
-    static constexpr int ENVS = 32;                    // envs per CTA: 4 warps x 8 groups
-    static constexpr int SMEM = ENVS * (2 * PS * 4 + 16 * KS);
+    static constexpr int ENVS = 32;                    // envs per CTA (L warps)
+    static constexpr int ROWS_BYTES = ENVS * 2 * PS * 4;
+    static constexpr int SMEM = ROWS_BYTES + ENVS * 16 * KS;
     static constexpr int FIT = 233472 / (SMEM + 1024);
     static constexpr int MINB = FIT > 7 ? 7 : (FIT < 1 ? 1 : FIT);
 };
@@ -46,29 +47,57 @@ __device__ __forceinline__ void cp8(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <int NCH>
-__global__ void __launch_bounds__(128, MwCfg<NCH>::MINB)
+// shared-memory accesses by 32-bit address: one base register per env, everything else is an immediate offset (with generic
+// pointers the compiler, at 72 registers, recomputed the row addresses from threadIdx at every access: 20 % of the instructions)
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float4 &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds1(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ldsu(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {
+    uint32_t y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+
+template <int NCH, int L>
+__global__ void __launch_bounds__(32 * L, MwCfg<NCH, L>::MINB)
 descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_t seed, ChildEntry *__restrict__ clists, int cap,
                   int gate_num, int gate_den, int fuse_expand) {
-    using C = MwCfg<NCH>;
+    using C = MwCfg<NCH, L>;
     constexpr int PS = C::PS, CPL = C::CPL, KS = C::KS;
-    constexpr int MW = 4;                              // 64-bit words of the children-of-this-node mask (T <= 256; else list walk)
+    constexpr int MW = 8;                              // 32-bit words of the children-of-this-node mask (T <= 256; else list walk)
+    constexpr uint32_t OWN = L == 4 ? 0x11111111u : 0x55555555u;   // node ids that are 0 mod L
     extern __shared__ float4 smem4[];
     const int A = t.A, T = t.T;
-    const int lane = threadIdx.x & 31, sub = lane & 3, gl = lane & ~3;
-    const unsigned gmask = 0xFu << gl;                 // the env's four lanes
-    const int slot = (threadIdx.x >> 5) * 8 + (lane >> 2);
-    // per env: [S terms in / running S sums out | g terms]; rows of one env are adjacent so that the chain lanes' accesses
-    // (lane 0: S row, lane 1: g row, of two envs per quarter-warp) fall into four different bank quartets
-    float *ps = reinterpret_cast<float *>(smem4) + slot * (2 * PS);
-    float *pg = ps + PS;
-    float4 *ps4 = reinterpret_cast<float4 *>(ps), *pg4 = reinterpret_cast<float4 *>(pg);
-    float4 *pe4 = smem4 + (C::ENVS * 2 * PS) / 4 + slot * KS;   // child entries {q, top, action | id << 8, flags}; raw records in flight
-    const uint32_t ps_addr = smem_u32(ps), pg_addr = smem_u32(pg), pe_addr = smem_u32(pe4);
+    const int lane = threadIdx.x & 31, sub = lane & (L - 1), gl = lane & ~(L - 1);
+    const unsigned gmask = ((1u << L) - 1u) << gl;     // the env's lanes
+    const int slot = threadIdx.x / L;
+    // per env two adjacent rows: [S terms in / running S sums out | g terms]; row pitch 4*NCH words, NCH odd, so the rows the
+    // chain lanes of a quarter-warp read (L = 2: S and g rows of four envs) start in different bank quartets
+    // (the two bases pass through an opaque move: otherwise the compiler re-derives them from the shared window / threadIdx at
+    // every access instead of keeping them in a register)
+    const uint32_t ps_addr = opaque(smem_u32(smem4) + (uint32_t)slot * (2 * PS * 4)), pg_addr = ps_addr + PS * 4;
+    const uint32_t pe_addr = opaque(smem_u32(smem4) + C::ROWS_BYTES + (uint32_t)slot * (16 * KS));   // child entries {q, top, action | id << 8, flags}
     const bl_qnorm qn(t.qrange + 2 * sim);
     const int nrow4 = t.AP >> 2;
     const int KW = (T + 63) >> 6;
-    const bool scan_ok = T <= 64 * MW;
+    const bool scan_ok = T <= 32 * MW;
+    const int KW32 = (T + 31) >> 5;
 
     int b = (int)blockIdx.x * C::ENVS + slot;
     if (b >= t.B) b = -1;
@@ -83,11 +112,11 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
 #pragma unroll
     for (int k = 0; k < 2 * CPL; k++) tp[k] = 0;
 
-    // child entry j of this lane lives in slot 4*j + sub (so a slot's owner is slot & 3)
+    // child entry j of this lane lives in slot L*j + sub (so a slot's owner is slot mod L)
     auto get = [&](int i) {
         ChildEntry e;
         if (i < KS) {
-            const float4 v = pe4[i];
+            const float4 v = lds4(pe_addr + 16u * i);
             e.q = v.x; e.top = v.y;
             const uint32_t u = __float_as_uint(v.z);
             e.a = u & 255; e.id = u >> 8; e.flags = __float_as_int(v.w);
@@ -95,7 +124,7 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
         return e;
     };
     auto put = [&](int i, const ChildEntry &e) {
-        if (i < KS) pe4[i] = make_float4(e.q, e.top, __uint_as_float((uint32_t)e.a | ((uint32_t)e.id << 8)), __int_as_float(e.flags));
+        if (i < KS) sts4(pe_addr + 16u * i, make_float4(e.q, e.top, __uint_as_float((uint32_t)e.a | ((uint32_t)e.id << 8)), __int_as_float(e.flags)));
         else cl[i] = e;
     };
     // asynchronous fetch of what a visit of node n needs at a known address: row summary -> pg[0..3], children mask ->
@@ -108,7 +137,7 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
         const float4 *row = reinterpret_cast<const float4 *>(t.pi + s * t.AP);
 #pragma unroll
         for (int k = 0; k < CPL; k++) {
-            const int c = 4 * k + sub;
+            const int c = L * k + sub;
             if (c < NCH && c < nrow4) cp16(ps_addr + 16u * c, row + c);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -130,18 +159,22 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
         if (passm == 0 || __popc(needm) * gate_den >= __popc(livem) * gate_num) {
             // ---- sample: l = #{a < A : sum[a] < r} over the running sums (descend_kernel, cuda.cu:160-176; see descend.cu) ----
             if (state == ST_SAMPLE) {
-                int cnt = 0;
+                // the sums are non-decreasing (every term is >= 0; entries past A repeat the last sum, so they only count when
+                // every sum is below r and the answer is last_nz anyway): whole chunks below r are counted by their last entry,
+                // four-way split over the lanes, then the one boundary chunk is counted entry by entry
+                int cb = 0;
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
-                    const int c = 4 * k + sub;
-                    if (c < NCH && c < nrow4) {
-                        const float4 v = ps4[c];
-                        const int a0 = 4 * c;
-                        cnt += (a0 < A && v.x < r) + (a0 + 1 < A && v.y < r) + (a0 + 2 < A && v.z < r) + (a0 + 3 < A && v.w < r);
-                    }
+                    const int c = L * k + sub;
+                    if (c < NCH) cb += lds1(ps_addr + 16u * c + 12u) < r ? 1 : 0;
                 }
-                cnt += __shfl_xor_sync(gmask, cnt, 1);
-                cnt += __shfl_xor_sync(gmask, cnt, 2);
+#pragma unroll
+                for (int o = 1; o < L; o <<= 1) cb += __shfl_xor_sync(gmask, cb, o);
+                int cnt = 4 * cb;
+                if (cb < NCH) {
+                    const float4 v = lds4(ps_addr + 16u * cb);
+                    cnt += (v.x < r) + (v.y < r) + (v.z < r);              // v.w >= r: the chunk is not wholly below
+                }
                 const int l = cnt, first_nz = nzpos & 255, last_nz = (nzpos >> 8) & 255;
                 action = first_nz == 255 ? -1 : (l < A ? (r <= 0.f ? first_nz : l) : last_nz);
                 state = ST_ADVANCE;
@@ -151,11 +184,11 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
                 parent = cur;
                 unsigned found = 0;
                 for (int j = 0; j < nown; j++) {
-                    const ChildEntry e = get(4 * j + sub);
+                    const ChildEntry e = get(L * j + sub);
                     if (e.a == action) found = 0x80000000u | ((unsigned)e.id << 16) | ((unsigned)e.flags & 0xffffu);
                 }
-                found |= __shfl_xor_sync(gmask, found, 1);
-                found |= __shfl_xor_sync(gmask, found, 2);
+#pragma unroll
+                for (int o = 1; o < L; o <<= 1) found |= __shfl_xor_sync(gmask, found, o);
                 const int next = (found >> 31) ? (int)((found >> 16) & 0x7fffu) : -1, nflags = (int)(found & 0xffffu);
                 cur = action >= 0 ? next : -1;
                 if (cur >= 0 && !(nflags >> 8)) { cur_seat = nflags & 255; state = ST_VISIT; prefetch_node(cur); }
@@ -182,37 +215,36 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
                 else r = bl_uniform_half_grid(bl_philox(seed ^ (t.counters[C_MOVE] * 0x9E3779B97F4A7C15ull), (uint64_t)b,
                                                         ((uint64_t)sim << 32) | (uint32_t)cur).x);
                 bl_aux ax;
-                { union { float4 f; bl_aux a; } x; x.f = pg4[0]; ax = x.a; }
+                { union { float4 f; bl_aux a; } x; x.f = lds4(pg_addr); ax = x.a; }
                 int N = 0;
                 nown = 0;
                 auto adopt = [&](const bl_node &ch, int id) {
-                    put(4 * nown + sub, ChildEntry{qn.fast(seat ? ch.w[1] : ch.w[0], ch.n), 0.f, (int)ch.relation, id,
+                    put(L * nown + sub, ChildEntry{qn.fast(seat ? ch.w[1] : ch.w[0], ch.n), 0.f, (int)ch.relation, id,
                                                    (int)ch.seat | ((int)ch.terminal << 8)});
                     N += ch.n;
                     nown++;
                 };
                 if (scan_ok) {
-                    // this lane's children = the mask bits whose node id is sub mod 4; their records are fetched together
+                    // this lane's children = the mask bits whose node id is sub mod L; their records are fetched together
                     // straight into the lane's entry slots, then adopted in place
-                    u64 mm[MW];
+                    uint32_t mm[MW];
 #pragma unroll
-                    for (int w = 0; w < MW; w++)
-                        mm[w] = w < KW ? *reinterpret_cast<const u64 *>(pg + 4 + 2 * w) & (0x1111111111111111ull << sub) : 0ull;
+                    for (int w = 0; w < MW; w++) mm[w] = w < KW32 ? ldsu(pg_addr + 16u + 4u * w) & (OWN << sub) : 0u;
                     int j = 0;
 #pragma unroll
                     for (int w = 0; w < MW; w++)
-                        for (u64 m = mm[w]; m; m &= m - 1) {
-                            const int id = w * 64 + __ffsll((long long)m) - 1, s = 4 * j + sub;
+                        for (uint32_t m = mm[w]; m; m &= m - 1) {
+                            const int id = w * 32 + __ffs((int)m) - 1, s = L * j + sub;
                             if (s < KS) cp16(pe_addr + 16u * s, t.node + node0 + id);
                             j++;
                         }
                     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 #pragma unroll
                     for (int w = 0; w < MW; w++)
-                        for (u64 m = mm[w]; m; m &= m - 1) {
-                            const int id = w * 64 + __ffsll((long long)m) - 1, s = 4 * nown + sub;
+                        for (uint32_t m = mm[w]; m; m &= m - 1) {
+                            const int id = w * 32 + __ffs((int)m) - 1, s = L * nown + sub;
                             bl_node ch;
-                            if (s < KS) { union { float4 f; bl_node n; } x; x.f = pe4[s]; ch = x.n; }
+                            if (s < KS) { union { float4 f; bl_node n; } x; x.f = lds4(pe_addr + 16u * s); ch = x.n; }
                             else ch = bl_ld_node(t.node + node0 + id);
                             adopt(ch, id);
                         }
@@ -220,14 +252,13 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
                     const bl_node nd = bl_ld_node(t.node + node0 + cur);
                     for (int c = nd.first_child; c >= 0;) {
                         const bl_node ch = bl_ld_node(t.node + node0 + c);
-                        if ((c & 3) == sub) adopt(ch, c);
+                        if ((c & (L - 1)) == sub) adopt(ch, c);
                         c = ch.next_sib;
                     }
                 }
-                N += __shfl_xor_sync(gmask, N, 1);
-                N += __shfl_xor_sync(gmask, N, 2);
-                nc = nown + __shfl_xor_sync(gmask, nown, 1);
-                nc += __shfl_xor_sync(gmask, nc, 2);
+                nc = nown;
+#pragma unroll
+                for (int o = 1; o < L; o <<= 1) { N += __shfl_xor_sync(gmask, N, o); nc += __shfl_xor_sync(gmask, nc, o); }
                 N += A - nc;                                        // every child-less action counts 1 (cuda.cu:91)
                 const float lambda = bl_lambda(c_puct, N, A);
                 nzpos = (uint32_t)ax.first_nz | ((uint32_t)ax.last_nz << 8);
@@ -235,19 +266,19 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
                 // max(RN(lambda*max_pi), 1e-4) (rounding is monotone); max is exact, so the group reduction is order-free
                 float alpha0 = fmaxf(__fmul_rn(lambda, ax.max_pi), 1.e-4f);
                 for (int j = 0; j < nown; j++) {
-                    ChildEntry e = get(4 * j + sub);
-                    e.top = __fmul_rn(lambda, ps[e.a]);             // the landed row still holds pi
+                    ChildEntry e = get(L * j + sub);
+                    e.top = __fmul_rn(lambda, lds1(ps_addr + 4u * e.a));   // the landed row still holds pi
                     alpha0 = fmaxf(alpha0, __fadd_rn(e.q, fmaxf(e.top, 1.e-4f)));
-                    put(4 * j + sub, e);
+                    put(L * j + sub, e);
                 }
-                alpha0 = fmaxf(alpha0, __shfl_xor_sync(gmask, alpha0, 1));
-                alpha0 = fmaxf(alpha0, __shfl_xor_sync(gmask, alpha0, 2));
+#pragma unroll
+                for (int o = 1; o < L; o <<= 1) alpha0 = fmaxf(alpha0, __shfl_xor_sync(gmask, alpha0, o));
                 const u64 lam2 = pk(lambda, lambda);
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {                   // top = lambda*pi, this lane's chunks of the landed row
-                    const int c = 4 * k + sub;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c < NCH && c < nrow4) v = ps4[c];
+                    const int c = L * k + sub;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);          // chunks past the row stay 0: their terms are +0 / -0, no-ops in the sums
+                    if (c < NCH && c < nrow4) v = lds4(ps_addr + 16u * c);
                     tp[2 * k] = mul2(pk(v.x, v.y), lam2); tp[2 * k + 1] = mul2(pk(v.z, v.w), lam2);
                 }
                 const bool tiny = __fmul_rn(lambda, bl_minnz(ax)) < BL_TINY;
@@ -267,8 +298,8 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
                 const u64 yS2 = pk(yS, yS), yG2 = pk(yG, yG), nbS2 = pk(-bS, -bS), bG2 = pk(bG, bG);
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
-                    const int c = 4 * k + sub;
-                    if (c < NCH && c < nrow4) {
+                    const int c = L * k + sub;
+                    if (c < NCH) {
                         const u64 t01 = tp[2 * k], t23 = tp[2 * k + 1];
                         u64 q = mul2(t01, yS2), rr = fma2(nbS2, q, t01);
                         const u64 s01 = fma2(rr, yS2, q);
@@ -278,8 +309,8 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
                         const u64 s23 = fma2(rr, yS2, q);
                         q = mul2(t23, yG2); rr = fma2(bG2, q, t23);
                         const u64 h23 = fma2(rr, yG2, q);
-                        ps4[c] = make_float4(lo(s01), hi(s01), lo(s23), hi(s23));
-                        pg4[c] = make_float4(lo(h01), hi(h01), lo(h23), hi(h23));
+                        sts4(ps_addr + 16u * c, make_float4(lo(s01), hi(s01), lo(s23), hi(s23)));
+                        sts4(pg_addr + 16u * c, make_float4(lo(h01), hi(h01), lo(h23), hi(h23)));
                     }
                 }
             }
@@ -287,11 +318,11 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
             bool bad = false;
             if (pass)
                 for (int j = 0; j < nown; j++) {
-                    const ChildEntry e = get(4 * j + sub);
+                    const ChildEntry e = get(L * j + sub);
                     const float bot = __fsub_rn(alpha, e.q), bb = __fmul_rn(bot, bot);
                     const float sv = bl_div_fast(e.top, bot), gv = bl_div_fast(-e.top, bb);
-                    ps[e.a] = sv;
-                    pg[e.a] = gv;
+                    sts1(ps_addr + 4u * e.a, sv);
+                    sts1(pg_addr + 4u * e.a, gv);
                     // bot outside [2^-60, 2^60] leaves the branch-free division's safe range; a negative / non-finite term would
                     // break the monotone running sums: both go to the exact serial path
                     bad |= !(bot >= 8.67e-19f && bot <= 1.15e18f) || !(sv >= 0.f && sv <= 3.0e38f);
@@ -306,18 +337,18 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
             if (slow) {
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
-                    const int c = 4 * k + sub;
-                    if (c < NCH) ps4[c] = make_float4(lo(tp[2 * k]), hi(tp[2 * k]), lo(tp[2 * k + 1]), hi(tp[2 * k + 1]));
+                    const int c = L * k + sub;
+                    if (c < NCH) sts4(ps_addr + 16u * c, make_float4(lo(tp[2 * k]), hi(tp[2 * k]), lo(tp[2 * k + 1]), hi(tp[2 * k + 1])));
                 }
             }
             __syncwarp();
             if (slow) {
-                auto topf = [&](int a) { return ps[a]; };
+                auto topf = [&](int a) { return lds1(ps_addr + 4u * a); };
                 auto qf = [&](int a) {
                     float q = 0.f;
-                    for (int s = 0; s < 4; s++) {
+                    for (int s = 0; s < L; s++) {
                         const int n_s = __shfl_sync(gmask, nown, gl + s);
-                        for (int j = 0; j < n_s; j++) { const ChildEntry e = get(4 * j + s); if (e.a == a) q = e.q; }
+                        for (int j = 0; j < n_s; j++) { const ChildEntry e = get(L * j + s); if (e.a == a) q = e.q; }
                     }
                     return q;
                 };
@@ -335,17 +366,21 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
         if (__any_sync(FULL, pass)) {
             float acc = 0.f;
             if (pass && sub < 2) {
-                float4 *row = sub ? pg4 : ps4;
+                // loads run AHEAD chunks in front of the additions; the S lane writes the running sums back over its terms
+                const uint32_t row = sub ? pg_addr : ps_addr;
+                constexpr int AHEAD = NCH < 4 ? NCH : 4;
+                float4 buf[AHEAD];
+#pragma unroll
+                for (int i = 0; i < AHEAD; i++) buf[i] = lds4(row + 16u * i);
 #pragma unroll
                 for (int c = 0; c < NCH; c++) {
-                    if (c < nrow4) {
-                        const float4 v = row[c];
-                        acc = __fadd_rn(acc, v.x); const float o0 = acc;
-                        acc = __fadd_rn(acc, v.y); const float o1 = acc;
-                        acc = __fadd_rn(acc, v.z); const float o2 = acc;
-                        acc = __fadd_rn(acc, v.w); const float o3 = acc;
-                        if (sub == 0) row[c] = make_float4(o0, o1, o2, o3);
-                    }
+                    const float4 v = buf[c % AHEAD];
+                    if (c + AHEAD < NCH) buf[c % AHEAD] = lds4(row + 16u * (c + AHEAD));
+                    acc = __fadd_rn(acc, v.x); const float o0 = acc;
+                    acc = __fadd_rn(acc, v.y); const float o1 = acc;
+                    acc = __fadd_rn(acc, v.z); const float o2 = acc;
+                    acc = __fadd_rn(acc, v.w); const float o3 = acc;
+                    if (sub == 0) sts4(row + 16u * c, make_float4(o0, o1, o2, o3));
                 }
             }
             __syncwarp();
@@ -370,14 +405,15 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
     }
     // ---- expand + env step of the group's env on its lane 0, in the env's (now dead) rows ----
     if (fuse_expand && b >= 0 && sub == 0)
-        bl_expand_one(t, sim, b, res_leaf, res_parent, res_action, reinterpret_cast<uint32_t *>(ps), reinterpret_cast<uint8_t *>(pg));
+        bl_expand_one(t, sim, b, res_leaf, res_parent, res_action, reinterpret_cast<uint32_t *>(reinterpret_cast<float *>(smem4) + slot * (2 * PS)),
+                      reinterpret_cast<uint8_t *>(reinterpret_cast<float *>(smem4) + slot * (2 * PS) + PS));
     bl_count(t.counters, C_EVALS, c_evals);
     bl_count(t.counters, C_CHILDREN, c_children);
     bl_count(t.counters, C_ITERS, c_iters);
     bl_count(t.counters, C_DESCENTS, (b >= 0 && sub == 0) ? 1u : 0u);
 }
 
-int g_mw_gate_num = 1, g_mw_gate_den = 2, g_mw_fuse = 1;
+int g_mw_gate_num = 1, g_mw_gate_den = 2, g_mw_fuse = 1, g_mw_lanes = 2;
 void read_mw_env() {
     static bool done = false;
     if (done) return;
@@ -387,15 +423,16 @@ void read_mw_env() {
         if (sscanf(e, "%d/%d", &a, &b) == 2 && a >= 0 && b > 0) { g_mw_gate_num = a; g_mw_gate_den = b; }
     }
     if (const char *e = getenv("BL_MW_FUSE")) g_mw_fuse = atoi(e);
+    if (const char *e = getenv("BL_MW_LANES")) g_mw_lanes = atoi(e) == 4 ? 4 : 2;
 }
 
-template <int NCH>
-int launch_mw(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st) {
-    using C = MwCfg<NCH>;
+template <int NCH, int L>
+int launch_mwl(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st) {
+    using C = MwCfg<NCH, L>;
     static bool ready = false;
     if (!ready) {
         if (C::SMEM > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(descend_mw_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(descend_mw_kernel<NCH, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
             if (e != cudaSuccess) return (int)e;
         }
         ready = true;
@@ -404,10 +441,15 @@ int launch_mw(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cu
     const int64_t envs = ((int64_t)t->B + 31) / 32 * 32;
     if (envs * cap * (int64_t)sizeof(ChildEntry) > t->scratch_bytes) return -3;
     const bool fused = g_mw_fuse && t->BP <= 16 * NCH;               // the env's rows hold a board + flood-fill stack
-    descend_mw_kernel<NCH><<<(unsigned)(envs / 32), 128, C::SMEM, st>>>(*t, sim, rands, seed, reinterpret_cast<ChildEntry *>(t->scratch), cap,
+    descend_mw_kernel<NCH, L><<<(unsigned)(envs / 32), 32 * L, C::SMEM, st>>>(*t, sim, rands, seed, reinterpret_cast<ChildEntry *>(t->scratch), cap,
                                                                        g_mw_gate_num, g_mw_gate_den, fused ? 1 : 0);
     if (cudaError_t e = cudaGetLastError()) return (int)e;
     return fused ? 0 : bl_expand_step(t, sim, st);
+}
+
+template <int NCH>
+int launch_mw(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st) {
+    return g_mw_lanes == 4 ? launch_mwl<NCH, 4>(t, sim, rands, seed, st) : launch_mwl<NCH, 2>(t, sim, rands, seed, st);
 }
 
 }  // namespace
