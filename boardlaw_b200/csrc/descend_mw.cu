@@ -413,7 +413,7 @@ descend_mw_kernel(bl_tree t, int sim, const bl_half *__restrict__ rands, uint64_
     bl_count(t.counters, C_DESCENTS, (b >= 0 && sub == 0) ? 1u : 0u);
 }
 
-int g_mw_gate_num = 1, g_mw_gate_den = 2, g_mw_fuse = 1, g_mw_lanes = 2;
+int g_mw_gate_num = 1, g_mw_gate_den = 2, g_mw_fuse = 1, g_mw_lanes = 0;     // lanes per env: 0 = 2 up to 9x9, 4 above (measured)
 void read_mw_env() {
     static bool done = false;
     if (done) return;
@@ -449,7 +449,8 @@ int launch_mwl(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, c
 
 template <int NCH>
 int launch_mw(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st) {
-    return g_mw_lanes == 4 ? launch_mwl<NCH, 4>(t, sim, rands, seed, st) : launch_mwl<NCH, 2>(t, sim, rands, seed, st);
+    const int lanes = g_mw_lanes ? g_mw_lanes : (t->A > 81 ? 4 : 2);
+    return lanes == 4 ? launch_mwl<NCH, 4>(t, sim, rands, seed, st) : launch_mwl<NCH, 2>(t, sim, rands, seed, st);
 }
 
 }  // namespace

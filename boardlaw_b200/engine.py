@@ -162,10 +162,36 @@ class SearchEngine:
             self.backup(sim)
         self.root(last)
 
+    _STATIC = ('in_board', 'in_seats', 'root_logits', 'root_v', 'out_logits', 'out_v', 'out_n_leaves')
+
+    def _search_partial(self, board, seats, network, **kwargs):
+        """A search over n < capacity envs in the same workspace (arena-style callers, boardlaw/arena/common.py:86-96, hand
+        the agent a different sub-batch every move): the arrays are env-major, so the first n envs' slices are a complete
+        workspace and only ``bl_tree.B`` changes.  Runs eagerly — a graph per sub-batch size would be captured once and
+        never replayed."""
+        n, cap = board.shape[0], self.B
+        self.scratch_for(network.packed())                        # sized at capacity, before B shrinks
+        saved = {k: getattr(self, k) for k in self._STATIC}
+        try:
+            self.B = self.ctree.B = n
+            for k, v in saved.items():
+                setattr(self, k, v[:n])
+            kwargs['use_graph'] = False
+            return tuple(x.clone() for x in self.search(board, seats, network, **kwargs))
+        finally:
+            self.B = self.ctree.B = cap
+            for k, v in saved.items():
+                setattr(self, k, v)
+
     def search(self, board, seats, network, c_puct=1 / 16, noise_eps=.25, alpha_scale=10, noise=None, use_graph=True):
         """One whole search (MCTS.__init__ + initialize + (n_nodes-1) x simulate + root).  Returns
-        (logits half (B,A), prior half (B,A), v half (B,2), n_leaves i64 (B,)) as views of static buffers."""
+        (logits half (B,A), prior half (B,A), v half (B,2), n_leaves i64 (B,)) as views of static buffers (copies when the
+        batch is smaller than the workspace)."""
         from .mcts import dirichlet_mix
+        if board.shape[0] < self.B:
+            return self._search_partial(board, seats, network, c_puct=c_puct, noise_eps=noise_eps, alpha_scale=alpha_scale, noise=noise)
+        if board.shape[0] != self.B:
+            raise ValueError(f'{board.shape[0]} envs do not fit a workspace of {self.B}')
         cparams = network.packed()
         self.in_board.copy_(board)
         self.in_seats.copy_(seats)
@@ -212,4 +238,4 @@ class SearchEngine:
             g.replay()
             self.launches += self._graph_launches[('sims',) + key]
         self.sim = self.T
-        return self.out_logits, self.ws.prior, self.out_v, self.out_n_leaves
+        return self.out_logits, self.ws.prior[:self.B], self.out_v, self.out_n_leaves

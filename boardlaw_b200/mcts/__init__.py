@@ -140,8 +140,8 @@ class EngineSearch:
     def __init__(self, eng, outputs):
         self.engine = eng
         self.device = eng.device
-        self.n_envs, self.n_nodes, self.n_seats, self.n_actions = eng.B, eng.T, eng.Sn, eng.A
-        self.envs = torch.arange(eng.B, device=eng.device)
+        self.n_envs, self.n_nodes, self.n_seats, self.n_actions = outputs[0].shape[0], eng.T, eng.Sn, eng.A   # <= the workspace's capacity
+        self.envs = torch.arange(self.n_envs, device=eng.device)
         self.sim = eng.T
         self._out = outputs
 
@@ -154,29 +154,35 @@ class EngineSearch:
 
     @property
     def tree(self):
-        ws = self.engine.ws
-        return arrdict.arrdict(children=self.engine.children_dense(), parents=ws.parents, relation=ws.relation)
+        ws, n = self.engine.ws, self.n_envs
+        return arrdict.arrdict(children=self.engine.children_dense()[:n], parents=ws.parents[:n], relation=ws.relation[:n])
 
     @property
     def stats(self):
-        return arrdict.arrdict(n=self.engine.ws.n, w=self.engine.ws.w)
+        return arrdict.arrdict(n=self.engine.ws.n[:self.n_envs], w=self.engine.ws.w[:self.n_envs])
 
     @property
     def transitions(self):
-        return arrdict.arrdict(rewards=self.engine.ws.rewards, terminal=self.engine.ws.terminal.bool())
+        return arrdict.arrdict(rewards=self.engine.ws.rewards[:self.n_envs], terminal=self.engine.ws.terminal[:self.n_envs].bool())
 
 
 _engines = {}
 
 
 def engine_for(world, n_nodes):
-    """Workspaces are persistent: one per (device, n_envs, boardsize, n_nodes), reused move after move."""
+    """Workspaces are persistent: one per (device, capacity, boardsize, n_nodes), reused move after move.  A batch smaller than
+    an existing workspace of the same shape runs inside it (``SearchEngine._search_partial``): arena-style callers, whose
+    sub-batch shrinks every move as games end, allocate once."""
     from ..engine import SearchEngine
     key = (str(world.device), world.n_envs, world.boardsize, n_nodes)
-    if key not in _engines:
-        if len(_engines) >= 4:                       # arena-style callers vary n_envs per call: bound the cache
-            _engines.pop(next(iter(_engines)))
-        _engines[key] = SearchEngine(world.n_envs, world.boardsize, n_nodes, world.device)
+    if key in _engines:
+        return _engines[key]
+    fits = [k for k in _engines if k[0] == key[0] and k[2:] == key[2:] and world.n_envs < k[1] <= 4 * max(world.n_envs, 256)]
+    if fits:
+        return _engines[min(fits, key=lambda k: k[1])]
+    if len(_engines) >= 4:
+        _engines.pop(next(iter(_engines)))
+    _engines[key] = SearchEngine(world.n_envs, world.boardsize, n_nodes, world.device)
     return _engines[key]
 
 

@@ -233,9 +233,11 @@ int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, const void 
 int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed,
                            bl_stream stream);
 
-/* Selects the descent kernel: 2 (default) = task-parallel descent with register-resident rows (descend.cu),
+/* Selects the descent kernel: 0 (default) = by board size (2 up to 9x9, 3 above: measured on c2/c3/c5),
+ * 2 = task-parallel descent, one lane per env with register-resident rows (descend.cu),
+ * 3 = two or four lanes per env: terms split over the lanes, the S and g chains on two of them (descend_mw.cu),
  * 1 = one lane per env in lock step, reference loops verbatim (engine.cu; kept as an on-device cross-check).
- * Both produce identical results. */
+ * All produce identical results (tests/test_gpu_mcts.py runs the oracle comparison for each). */
 int bl_debug_set_descend_variant(int variant);
 
 /* Phase clock of the descent and network kernels: when `buf` (32 x uint64 on the device, zeroed by the caller) is non-NULL every warp adds the

@@ -208,3 +208,19 @@ def check_mcts_kats(ops):
     assert w == [1., 1.] and n == [1, 1]
     w, n = bk([[0.], [1.], [2.]], [[0.], [0.], [0.]], [0, 0, 0], [[0.], [3.], [0.]], [-1, 0, 1], [False, True, False], 2)
     assert w == [3., 3., 2.]
+
+
+class KthValid:
+    """Deterministic agent for the arena fixtures: plays the k-th legal move with k = (mult * sum(board) + 5 * seat) mod
+    #legal — a function of the position only, in integer arithmetic, so the reference's CPU env and the GPU env play the
+    same games.  Works on any world with ``board``, ``seats`` and ``valid``."""
+
+    def __init__(self, mult):
+        self.mult = mult
+
+    def __call__(self, world, eval=False, value=True):
+        valid = world.valid
+        n = valid.sum(-1)
+        k = (self.mult * world.board.long().flatten(1).sum(-1) + 5 * world.seats.long()) % n.clamp(min=1)
+        hit = (valid.long().cumsum(-1) == (k + 1)[:, None]) & valid
+        return types.SimpleNamespace(actions=hit.long().argmax(-1))

@@ -120,7 +120,7 @@ def test_engine_stepwise_vs_oracle(S, B, T, W, D, extreme, variant):
     try:
         _engine_stepwise_vs_oracle(S, B, T, W, D, extreme)
     finally:
-        _lib.lib().bl_debug_set_descend_variant(2)
+        _lib.lib().bl_debug_set_descend_variant(0)
 
 
 def test_shared_reciprocal_division():
