@@ -309,3 +309,42 @@ def synth_state_dict(S, W, D, seed=0):
     sd['policy.core.weight'], sd['policy.core.bias'] = lin(A, W)
     sd['value.core.weight'], sd['value.core.bias'] = lin(1, W)
     return sd
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# arena (boardlaw/arena/common.py:50-106) — restated on HexWorld; pinned by tests/golden/arena.npz, which holds the results of
+# the reference's own evaluate() on the same positions and agents (tests/golden/make_golden_arena.py)
+# ---------------------------------------------------------------------------------------------------------------
+def matchup_indices(n_envs, n_seats):                             # common.py:50-55
+    from itertools import permutations
+    patterns = torch.as_tensor(list(permutations(range(n_seats))))
+    return patterns, patterns.repeat((n_envs // len(patterns), 1))
+
+
+def evaluate(world, agents):                                      # common.py:75-106, 57-73
+    """agents: list of (name, agent(world, eval=True) -> .actions).  Returns per seat pattern (names, wins per seat, moves,
+    games)."""
+    B = world.n_envs
+    patterns, matchup = matchup_indices(B, world.n_seats)
+    envs = torch.arange(B)
+    terminal = torch.zeros(B, dtype=torch.bool)
+    wins = torch.zeros((B, world.n_seats), dtype=torch.int)
+    moves = torch.zeros(B, dtype=torch.int)
+    board, seats = world.board.clone(), world.seats.clone()
+    while not terminal.all():
+        for i, (_, agent) in enumerate(agents):
+            mask = (matchup[envs, seats.long()] == i) & ~terminal                       # common.py:90
+            if mask.any():
+                sub = HexWorld(board[mask], seats[mask], world.ops)
+                new, trans = sub.step(agent(sub, eval=True).actions)                     # common.py:93-94
+                board[mask], seats[mask] = new.board, new.seats
+                terminal[mask] = trans.terminal
+                wins[mask] += (trans.rewards == 1).int()                                # common.py:98-99
+                moves[mask] += 1
+    out = []
+    for p in patterns:                                                                   # common.py:61-72
+        rows = (matchup == p).all(-1)
+        w = wins[rows].sum(0)
+        out.append(types.SimpleNamespace(names=tuple(agents[int(i)][0] for i in p), wins=tuple(float(x) for x in w),
+                                         moves=float(moves[rows].sum()), games=float(w.sum())))
+    return out
