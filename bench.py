@@ -302,6 +302,7 @@ def run_ours(args):
                                   'newton_iters_per_eval': counters[2] / max(counters[0], 1)}
 
         cpu = cpu_baseline(args.config, sd, steps=3, warmup=1) if (world == 1 and not args.no_cpu) else None
+        refcuda = reference_cuda_baseline(args.config, sd) if (world == 1 and not args.no_cpu) else None
         result = {
             'metric': 'MCTS sims/sec', 'value': value, 'unit': 'sims/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -318,6 +319,7 @@ def run_ours(args):
             'clocks': clocks.summary(),
             'roofline': roofline,
             'cpu_baseline': cpu,
+            'reference_cuda': refcuda,
         }
         if world > 1:
             result['config']['allgather_bytes_per_rank_per_move'] = B * record_width(A)
@@ -363,6 +365,46 @@ def cpu_baseline(config, sd, steps, warmup):
                       + ('reference CPU kernels built from its unmodified sources at the reference loader\'s flags (-O0), '
                          'single-threaded per-env loops as in the reference, torch ops on all threads; Python orchestration restated (oracle/pyref.py)'
                          if kind == 'reference' else 'C restatement of the reference kernels (oracle/boardlaw_oracle.c, -O2)')}
+
+
+def reference_cuda_baseline(config, sd, steps=2, warmup=1):
+    """The reference's own CUDA kernels (oracle/_ref/CUDA: its unmodified sources compiled for sm_100a by its loader's recipe,
+    oracle/build_ref.py) under the restated Python orchestration, on this GPU, on a bounded sample — SURVEY.md 8(c)/(d)'s
+    "second baseline".  An extra, informational figure: the contract's reference arm stays the CPU one.  None when the build is
+    absent."""
+    import torch
+    from oracle import build_ref, pyref
+    if not build_ref.available('CUDA'):
+        return None
+    try:
+        S, B, T, W, D = CONFIGS[config]
+        Bc = min({'c3': 16384}.get(config, 32768), B)      # the whole batch where it fits: the reference's path is launch-bound, a small sample would flatter us
+        dev = torch.device('cuda', torch.cuda.current_device())
+        ops = pyref.RefCudaOps()
+        torch.manual_seed(0)
+        w = pyref.HexWorld.initial(Bc, S, ops, device=dev)
+        for _ in range(2 * S * S):
+            w, _ = w.step(torch.multinomial(w.valid.float(), 1).squeeze(-1))
+        net = pyref.FCNet(sd, device=dev)
+
+        def move(w):
+            d = pyref.agent_call(w, net, n_nodes=T, c_puct=1 / 16)
+            w2, _ = w.step(d.actions)
+            return w2
+        for _ in range(warmup):
+            w = move(w)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            w = move(w)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {'value': Bc * T * steps / dt, 'unit': 'sims/s', 'seconds': dt,
+                'sample': f'{steps} moves of {Bc} envs (of {B}) at {describe(config)}: the reference\'s CUDA kernels (unmodified sources, '
+                          'its loader\'s flags with -std=c++17) + torch ops under autocast as in its MCTS.simulate, Python orchestration '
+                          'restated (oracle/pyref.py); wall clock with synchronize on both sides'}
+    except Exception as e:                      # informational leg: never takes the bench line down
+        return {'unavailable': f'{type(e).__name__}: {e}'[:300]}
 
 
 def run_reference(args):

@@ -65,6 +65,9 @@ SIGNATURES = {
     'bl_tree_eval_root': (c_int, [POINTER(Tree), POINTER(FCParams), P, P, P, P]),
     'bl_tree_root': (c_int, [POINTER(Tree), c_int, P, P, P, P, P]),
     'bl_tree_children_dense': (c_int, [POINTER(Tree), P, P]),
+    'bl_reward_to_go': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    'bl_policy_value_loss': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, P]),
+    'bl_adam_step': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, P]),
 }
 
 _lib = None

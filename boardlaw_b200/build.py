@@ -30,6 +30,7 @@ SOURCES = {
     'net.cu': [],
     'net_tc.cu': [],
     'net_tc_wide.cu': [],
+    'learner.cu': [],
     'host.cu': [],
 }
 

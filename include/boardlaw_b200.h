@@ -276,6 +276,28 @@ int bl_tree_root(const bl_tree *t, int sim, const bl_half *log_lut, bl_half *log
 /* Materialises the reference's dense children (B,T,A) i16 tensor from the child lists. */
 int bl_tree_children_dense(const bl_tree *t, int16_t *children, bl_stream stream);
 
+/* ---- learner side: the consumers of the self-play trajectories ------------------------------------------ */
+
+/* learning.reward_to_go (boardlaw/learning.py:57-76, called from main.as_chunk, boardlaw/main.py:61-67) over one chunk:
+ * reward, value (T,B,Sn) f32, terminal (T,B) u8 (bool; the reference stacks it over the seats), out (T,B,Sn) f32, or half when
+ * out_is_half (as_chunk's `.half()`).  out[T-1] = terminal ? reward : value; out[t] = terminal[t] ? reward[t] :
+ * reward[t] + gamma*out[t+1], fp32 with the product rounded before the sum: bit-identical to the reference's loop.
+ * Unlike the reference it does not write the fallback into `value`. */
+int bl_reward_to_go(const float *reward, const float *value, const uint8_t *terminal, void *out, int out_is_half,
+                    int T, int B, int Sn, float gamma, bl_stream stream);
+
+/* The loss of main.optimize (boardlaw/main.py:86-101) and its gradient in one pass: logp (N,A) f32 masked log-softmax output
+ * of the network, v (N,2) f32, target_logits (N,A) half, target_v (N,2) half (reward-to-go), seats (N,) i32.
+ * sums[0] += sum_n sum_a exp(l0)*l (policy_loss = -sums[0]/N), sums[1] += sum (target - v)^2 (value_loss = sums[1]/(2N));
+ * dscores (N,A) f32 = d(policy_loss + value_loss)/d(pre-softmax scores), dz (N,) f32 = d/d(pre-tanh value). */
+int bl_policy_value_loss(const float *logp, const float *v, const bl_half *target_logits, const bl_half *target_v,
+                         const int32_t *seats, float *dscores, float *dz, float *sums, int N, int A, bl_stream stream);
+
+/* torch.optim.Adam's update (boardlaw/main.py:154, defaults: no weight decay, no amsgrad) over one flat fp32 buffer of n
+ * parameters; step counts from 1. */
+int bl_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                 float beta2, float eps, int step, bl_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

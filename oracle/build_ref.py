@@ -71,6 +71,42 @@ def build(verbose=False):
     return True
 
 
+def build_cuda(verbose=False):
+    """Variant ``CUDA``: the reference's CUDA kernels (``wrappers.cpp`` + ``cuda.cu`` of each module) for sm_100a, by the recipe of
+    its own loader (``boardlaw/cuda.py:10-27`` ``load_cuda``: ``--use_fast_math -lineinfo``) with one flag changed, ``-std=c++14``
+    -> ``-std=c++17`` for the device compile, because the ATen headers of the installed torch refuse C++14.  nvcc
+    cross-compiles here without a GPU; ~5 minutes.  Only ``bench.py``'s ``reference_cuda`` leg loads the result."""
+    if not REFERENCE.exists():
+        return False
+    import sysconfig
+    import torch.utils.cpp_extension as ext
+    [torch_libdir] = ext.library_paths()
+    python_libdir = sysconfig.get_config_var('LIBDIR')
+    libpython_ver = sysconfig.get_config_var('LDVERSION')
+    os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
+    for name, rel in MODULES.items():
+        if so_path(name, 'CUDA').exists():
+            continue
+        bdir = REF_OUT / 'CUDA' / name
+        bdir.mkdir(parents=True, exist_ok=True)
+        src = (REFERENCE / rel).parent
+        ext.load(
+            name=modname(name, 'CUDA'),
+            sources=[str(src / 'wrappers.cpp'), str(src / 'cuda.cu')],
+            extra_cflags=['-std=c++17'],
+            extra_cuda_cflags=['--use_fast_math', '-lineinfo', '-std=c++17'],
+            extra_include_paths=['/usr/local/cuda/include'],
+            with_cuda=True,
+            extra_ldflags=[
+                f'-lpython{libpython_ver}', '-ltorch', '-ltorch_python', '-lc10_cuda', '-lc10',
+                f'-L{torch_libdir}', f'-Wl,-rpath,{torch_libdir}',
+                f'-L{python_libdir}', f'-Wl,-rpath,{python_libdir}'],
+            build_directory=str(bdir),
+            verbose=verbose,
+            is_python_module=False)
+    return True
+
+
 _loaded = {}
 
 
@@ -97,6 +133,8 @@ def available(variant='O0'):
 
 if __name__ == '__main__':
     ok = build(verbose='-v' in sys.argv)
+    if '--cuda' in sys.argv:
+        build_cuda(verbose='-v' in sys.argv)
     print('built' if ok else 'reference sources not present; nothing built')
     for v in VARIANTS:
         for n in MODULES:

@@ -51,6 +51,24 @@ class COps:
         return _c.root(m, pow_mode=self.pow_mode)
 
 
+class RefCudaOps:
+    """The reference's own CUDA extension built for sm_100a from its unmodified sources (oracle/build_ref.py, variant CUDA: its
+    loader's flags with -std=c++14 -> c++17, which torch 2.x headers require).  Used only by bench.py's
+    ``reference_cuda`` leg to time the reference's kernels on the same GPU."""
+    name = 'reference-cuda'
+
+    def __init__(self):
+        from . import build_ref
+        self.hex = build_ref.load('hexcuda', 'CUDA')
+        self.mcts = build_ref.load('mctscuda', 'CUDA')
+        self.step, self.observe = self.hex.step, self.hex.observe
+        self.MCTS, self.Backup, self.backup = self.mcts.MCTS, self.mcts.Backup, self.mcts.backup
+        self.root = self.mcts.root
+
+    def descend(self, m, rands=None):
+        return self.mcts.descend(m)
+
+
 class RefOps:
     """The reference's own CPU extension (oracle/_ref), unmodified sources."""
     name = 'reference'
@@ -84,9 +102,9 @@ class HexWorld:
         self._obs = self._valid = None
 
     @classmethod
-    def initial(cls, n_envs, boardsize=11, ops=None):
-        return cls(torch.zeros((n_envs, boardsize, boardsize), dtype=torch.uint8),
-                   torch.zeros((n_envs,), dtype=torch.int32), ops)
+    def initial(cls, n_envs, boardsize=11, ops=None, device='cpu'):
+        return cls(torch.zeros((n_envs, boardsize, boardsize), dtype=torch.uint8, device=device),
+                   torch.zeros((n_envs,), dtype=torch.int32, device=device), ops)
 
     @property
     def obs(self):
@@ -109,7 +127,7 @@ class HexWorld:
         if reset:
             terminal = (rewards > 0).any(-1)
         else:
-            terminal = torch.zeros((self.n_envs,), dtype=torch.bool)
+            terminal = torch.zeros((self.n_envs,), dtype=torch.bool, device=self.board.device)
         new_board[terminal] = 0
         new_seat = 1 - self.seats
         new_seat[terminal] = 0
@@ -169,11 +187,12 @@ def fc_forward(sd, obs, valid, seats):
 class FCNet:
     """Callable network over HexWorld, holding a reference-format state dict."""
 
-    def __init__(self, sd):
-        self.sd = {k: v.detach().float() for k, v in sd.items()}
+    def __init__(self, sd, device='cpu'):
+        self.sd = {k: v.detach().float().to(device) for k, v in sd.items()}
 
     def __call__(self, world):
-        with torch.no_grad():
+        # on a CUDA device (bench.py's reference-kernels-on-this-GPU leg only) under autocast, as mcts/__init__.py:131-132
+        with torch.no_grad(), torch.autocast('cuda', enabled=world.board.device.type == 'cuda'):
             return fc_forward(self.sd, world.obs, world.valid, world.seats)
 
 
@@ -183,7 +202,7 @@ class FCNet:
 
 def dirichlet_noise(logits, valid, eps, alpha_scale=10):          # mcts/__init__.py:13-24
     alpha = alpha_scale / logits.size(-1)
-    alpha = torch.full((valid.shape[-1],), alpha, dtype=torch.float)
+    alpha = torch.full((valid.shape[-1],), alpha, dtype=torch.float, device=logits.device)
     draw = torch.distributions.Dirichlet(alpha).sample(logits.shape[:-1])
     draw[~valid] = 0.
     draw = draw / draw.sum(-1, keepdims=True)
@@ -198,19 +217,20 @@ class Tree:
         A, Sn = S * S, world.n_seats
         self.ops = world.ops
         self.B, self.T, self.A, self.Sn = B, T, A, Sn
-        self.envs = torch.arange(B)
-        self.children = torch.full((B, T, A), -1, dtype=torch.int16)
-        self.parents = torch.full((B, T), -1, dtype=torch.int16)
-        self.relation = torch.full((B, T), -1, dtype=torch.int16)
+        dev = world.board.device
+        self.envs = torch.arange(B, device=dev)
+        self.children = torch.full((B, T, A), -1, dtype=torch.int16, device=dev)
+        self.parents = torch.full((B, T), -1, dtype=torch.int16, device=dev)
+        self.relation = torch.full((B, T), -1, dtype=torch.int16, device=dev)
         self.board = world.board[:, None].repeat(1, T, 1, 1).contiguous()
         self.seats = world.seats[:, None].repeat(1, T).contiguous()
-        self.rewards = torch.zeros((B, T, Sn), dtype=torch.float16)
-        self.terminal = torch.zeros((B, T), dtype=torch.bool)
-        self.logits = torch.full((B, T, A), np.nan, dtype=torch.float16)
-        self.v = torch.full((B, T, Sn), np.nan, dtype=torch.float16)
-        self.n = torch.zeros((B, T), dtype=torch.int16)
-        self.w = torch.zeros((B, T, Sn), dtype=torch.float16)
-        self.c_puct = torch.full((B,), c_puct, dtype=torch.float16)
+        self.rewards = torch.zeros((B, T, Sn), dtype=torch.float16, device=dev)
+        self.terminal = torch.zeros((B, T), dtype=torch.bool, device=dev)
+        self.logits = torch.full((B, T, A), np.nan, dtype=torch.float16, device=dev)
+        self.v = torch.full((B, T, Sn), np.nan, dtype=torch.float16, device=dev)
+        self.n = torch.zeros((B, T), dtype=torch.int16, device=dev)
+        self.w = torch.zeros((B, T, Sn), dtype=torch.float16, device=dev)
+        self.c_puct = torch.full((B,), c_puct, dtype=torch.float16, device=dev)
         self.noise_eps, self.alpha_scale = noise_eps, alpha_scale
         self.sim = 0
         self.hooks = hooks
@@ -348,3 +368,48 @@ def evaluate(world, agents):                                      # common.py:75
         out.append(types.SimpleNamespace(names=tuple(agents[int(i)][0] for i in p), wins=tuple(float(x) for x in w),
                                          moves=float(moves[rows].sum()), games=float(w.sum())))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# learner (boardlaw/learning.py:57-76, boardlaw/main.py:75-101) — restated on CPU tensors; reward_to_go is pinned against the
+# reference's own function (tests/test_learner.py, where /root/reference exists) and its KATs (learning.py:83-94)
+# ---------------------------------------------------------------------------------------------------------------
+def present_value(deltas, fallback, terminal, alpha):            # learning.py:57-68
+    result = torch.full_like(fallback, np.nan)
+    result[-1] = fallback[-1]
+    for t in range(deltas.size(0) - 1, -1, -1):
+        result[t] = torch.where(terminal[t], fallback[t], deltas[t] + alpha * result[t + 1])
+    return result
+
+
+def reward_to_go(reward, value, terminal, gamma=1.):             # learning.py:70-76
+    fallback = value.clone()                                      # (the reference writes into `value` itself)
+    fallback[terminal] = reward[terminal]
+    return present_value(reward[:-1], fallback, terminal, gamma)
+
+
+def learner_loss(sd, world, target_logits, target_v):            # main.py:86-99, fp32
+    """(policy_loss, value_loss) of the network ``sd`` on ``world`` with autograd enabled on ``sd``'s tensors."""
+    d = fc_forward(sd, world.obs, world.valid, world.seats)
+    zeros = torch.zeros_like(d.logits)
+    l = d.logits.where(d.logits > -np.inf, zeros)
+    l0 = target_logits.float().where(target_logits > -np.inf, zeros)
+    policy_loss = -(l0.exp() * l).sum(-1).mean()
+    value_loss = (target_v.float() - d.v).square().mean()
+    return policy_loss, value_loss
+
+
+def learner_step(sd, world, target_logits, target_v, lr=1e-3, steps=1):
+    """``steps`` iterations of main.optimize's update with torch autograd + torch.optim.Adam in fp32 on the CPU.  Returns
+    (new state dict, gradients of the first step, (policy_loss, value_loss) of the first step)."""
+    params = {k: v.detach().clone().float().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=lr)
+    first = None
+    for _ in range(steps):
+        pl, vl = learner_loss(params, world, target_logits, target_v)
+        opt.zero_grad()
+        (pl + vl).backward()
+        if first is None:
+            first = ({k: p.grad.detach().clone() for k, p in params.items()}, (pl.detach(), vl.detach()))
+        opt.step()
+    return {k: p.detach() for k, p in params.items()}, first[0], first[1]

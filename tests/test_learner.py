@@ -1,0 +1,157 @@
+"""Learner-side kernels: reward-to-go scan (bit-exact), fused policy/value loss + gradient, Adam, and the
+written-out backward of FCModel — against the oracle's CPU restatement (torch autograd / torch.optim.Adam in fp32), which is
+itself pinned against the reference's own ``learning.reward_to_go`` and its known answers (boardlaw/learning.py:83-94)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyref, refpy
+
+
+def _rtg_case(T, B, Sn, seed, p_term=.1):
+    g = torch.Generator().manual_seed(seed)
+    reward = (torch.rand((T, B, Sn), generator=g) < .1).float() * (torch.randint(0, 2, (T, B, Sn), generator=g) * 2 - 1)
+    value = torch.rand((T, B, Sn), generator=g) * 2 - 1
+    terminal = torch.rand((T, B), generator=g) < p_term
+    return reward, value, terminal
+
+
+def test_oracle_reward_to_go_known_answers():
+    """boardlaw/learning.py:83-94."""
+    reward, value = torch.tensor([1., 2., 3.]), torch.tensor([4., 5., 6.])
+    out = pyref.reward_to_go(reward, value, torch.tensor([False, False, False]), 1.)
+    assert out.tolist() == [9., 8., 6.]
+    out = pyref.reward_to_go(reward, value, torch.tensor([False, True, False]), 1.)
+    assert out.tolist() == [3., 2., 6.]
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refpy.present(), reason='reference sources not present')
+def test_oracle_reward_to_go_vs_reference():
+    import sys
+    refpy.load()
+    import boardlaw.learning as rl
+    for T, B, Sn, seed, gamma in [(64, 96, 2, 0, 1.), (9, 33, 2, 1, .97), (2, 5, 1, 2, 1.)]:
+        reward, value, terminal = _rtg_case(T, B, Sn, seed)
+        term = torch.stack([terminal] * Sn, -1)
+        want = rl.reward_to_go(reward.clone(), value.clone(), term, gamma)
+        got = pyref.reward_to_go(reward, value, term, gamma)
+        assert torch.equal(want.view(torch.int32), got.view(torch.int32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('T,B,Sn,seed,gamma', [(64, 4096, 2, 0, 1.), (9, 33, 2, 1, .97), (2, 5, 1, 2, 1.), (1, 7, 2, 3, 1.), (64, 1, 2, 4, .5)])
+def test_reward_to_go_bit_exact(T, B, Sn, seed, gamma):
+    from boardlaw_b200 import learner
+    reward, value, terminal = _rtg_case(T, B, Sn, seed)
+    term = torch.stack([terminal] * Sn, -1)
+    want = pyref.reward_to_go(reward, value, term, gamma)
+    v_dev = value.cuda()
+    got = learner.reward_to_go(reward.cuda(), v_dev, term.cuda(), gamma)
+    assert torch.equal(got.cpu().view(torch.int32), want.view(torch.int32))
+    assert torch.equal(v_dev.cpu(), value)                                     # inputs untouched
+    got_h = learner.reward_to_go(reward.cuda(), value.cuda(), terminal.cuda(), gamma, half=True)      # terminal without the seat axis
+    assert torch.equal(got_h.cpu().view(torch.int16), want.half().view(torch.int16))
+
+
+@pytest.mark.gpu
+def test_reward_to_go_known_answers_and_empty():
+    from boardlaw_b200 import learner
+    reward, value = torch.tensor([1., 2., 3.]).cuda(), torch.tensor([4., 5., 6.]).cuda()
+    assert learner.reward_to_go(reward, value, torch.tensor([False, False, False]).cuda()).tolist() == [9., 8., 6.]
+    assert learner.reward_to_go(reward, value, torch.tensor([False, True, False]).cuda()).tolist() == [3., 2., 6.]
+    e = torch.zeros((4, 0, 2)).cuda()
+    assert learner.reward_to_go(e, e, torch.zeros((4, 0), dtype=torch.bool).cuda()).shape == (4, 0, 2)
+
+
+def _batch(S, N, seed):
+    """N positions from random playouts, search-like targets: a noisy softmax over the legal moves, reward-to-go in [-1, 1]."""
+    import gpu_util as gu
+    w = gu.start_position(S, N, S * S // 3, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    raw = torch.randn((N, S * S), generator=g) * 2
+    tl = torch.log_softmax(raw.masked_fill(~w.valid, -np.inf), -1).half()
+    t = torch.rand((N,), generator=g) * 2 - 1
+    tv = torch.stack([t, -t], -1).half()
+    return w, tl, tv
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('S,W,D,N', [(5, 32, 2, 300), (9, 64, 3, 1000)])
+def test_loss_and_gradients_vs_autograd(S, W, D, N):
+    """Fused loss kernel + written-out backward against torch autograd on the oracle's fp32 CPU network.  Tolerance: rtol 1e-3 /
+    atol 1e-6 on gradients (different summation orders over N samples in fp32), 1e-5 relative on the losses."""
+    from boardlaw_b200 import arrdict, heads, learner
+    from boardlaw_b200.hex import Hex
+    from boardlaw_b200.networks import FCModel
+    sd = pyref.synth_state_dict(S, W, D, seed=7)
+    w, tl, tv = _batch(S, N, 11)
+    _, grads, (pl, vl) = pyref.learner_step(sd, w, tl, tv)
+    net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(S * S), width=W, depth=D)
+    net.load_state_dict(sd)
+    L = learner.Learner(net.cuda())
+    batch = arrdict.arrdict(worlds=Hex(board=w.board.cuda(), seats=w.seats.cuda()), decisions=arrdict.arrdict(logits=tl.cuda()),
+                            reward_to_go=tv.cuda())
+    gpl, gvl = L.forward_backward(batch)
+    assert abs(float(gpl) - float(pl)) <= 1e-5 * abs(float(pl)) + 1e-6
+    assert abs(float(gvl) - float(vl)) <= 1e-5 * abs(float(vl)) + 1e-6
+    for k, want in grads.items():
+        got = L.g[k].cpu()
+        assert got.shape == want.shape, k
+        err = (got - want).abs()
+        assert bool((err <= 1e-3 * want.abs() + 1e-6).all()), f'{k}: max err {float(err.max()):.3e} (max |g| {float(want.abs().max()):.3e})'
+
+
+@pytest.mark.gpu
+def test_adam_vs_torch():
+    """bl_adam_step against torch.optim.Adam on identical injected gradients, 5 steps."""
+    from boardlaw_b200 import heads, learner
+    from boardlaw_b200.networks import FCModel
+    S, W, D = 5, 32, 2
+    sd = pyref.synth_state_dict(S, W, D, seed=3)
+    net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(S * S), width=W, depth=D)
+    net.load_state_dict(sd)
+    L = learner.Learner(net.cuda(), lr=1e-3)
+    ref = L.flat.detach().cpu().clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(5):
+        grad = torch.randn(ref.shape, generator=g) * 10 ** torch.randint(-6, 1, ref.shape, generator=g).float()
+        ref.grad = grad.clone()
+        opt.step()
+        L.grad.copy_(grad)
+        L.apply()
+        assert torch.allclose(L.flat.cpu(), ref.detach(), rtol=1e-6, atol=1e-8)
+    assert L.step == 5
+
+
+@pytest.mark.gpu
+def test_optimize_updates_the_network_the_search_uses():
+    """Three optimiser steps: parameters track the oracle's (autograd + torch Adam), the loss goes down, and the inference
+    kernels (the self-play path) serve the updated weights — the packed operands are restaged."""
+    from boardlaw_b200 import arrdict, heads, learner
+    from boardlaw_b200.hex import Hex
+    from boardlaw_b200.networks import FCModel
+    S, W, D, N = 5, 32, 2, 512
+    sd = pyref.synth_state_dict(S, W, D, seed=5)
+    w, tl, tv = _batch(S, N, 21)
+    new_sd, _, (pl0, vl0) = pyref.learner_step(sd, w, tl, tv, lr=1e-3, steps=3)
+    net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(S * S), width=W, depth=D)
+    net.load_state_dict(sd)
+    net = net.cuda()
+    worlds = Hex(board=w.board.cuda(), seats=w.seats.cuda())
+    before = net(worlds).logits.clone()
+    L = learner.Learner(net, lr=1e-3)
+    batch = arrdict.arrdict(worlds=worlds, decisions=arrdict.arrdict(logits=tl.cuda()), reward_to_go=tv.cuda())
+    losses = [L.optimize(batch) for _ in range(3)]
+    assert float(losses[-1].policy_loss + losses[-1].value_loss) < float(losses[0].policy_loss + losses[0].value_loss)
+    assert abs(float(losses[0].policy_loss) - float(pl0)) < 1e-4 and abs(float(losses[0].value_loss) - float(vl0)) < 1e-4
+    for k, want in new_sd.items():
+        got = dict(net.named_parameters())[k].detach().cpu()
+        # Adam's first steps move every weight by ~lr whatever the gradient's size: 3 steps of 1e-3, agreement to 2 % of a step
+        assert float((got - want).abs().max()) < 6e-5, k
+    after = net(worlds)
+    want = pyref.FCNet(new_sd)(w)
+    assert not torch.equal(after.logits, before)
+    fin = torch.isfinite(want.logits)
+    assert float((after.logits.cpu()[fin] - want.logits[fin]).abs().max()) < 2e-3      # weights agree to 6e-5, not bit for bit

@@ -16,7 +16,7 @@ for l in open(sass):
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
     if m: lines.append((cur, m.group(2)))
 src = open('boardlaw_b200/csrc/descend_mw.cu').read().split('\n')
-def find(s): return next(i + 1 for i, l in enumerate(src) if s in l)
+def find(s): return next(i + 1 for i, l in enumerate(src) if l.strip().startswith(s))
 marks = [(find('while (true) {'), 'loop head + gate'), (find('if (state == ST_SAMPLE)'), 'sample'), (find('if (state == ST_ADVANCE)'), 'advance'),
          (find('if (state == ST_DONE)'), 'done + wait'), (find('if (visit) {'), 'visit'), (find('bool pass = state'), 'terms'),
          (find('bool bad = false;'), 'child terms'), (find('const bool slow = state'), 'slow path'), (find('pass = state == ST_PASS'), 'chain'),
