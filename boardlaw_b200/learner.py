@@ -132,3 +132,20 @@ class Learner:
         pl, vl = self.forward_backward(batch)
         self.apply()
         return arrdict.arrdict(policy_loss=pl, value_loss=vl)
+
+
+def chunk_from_records(records, boardsize, batch_size=None):
+    """The learner's chunk from the all-gathered trajectory records (``selfplay.TrajectoryPool.wait()``: one (world, B, R)
+    uint8 tensor per buffered move) — the same structure ``as_chunk`` builds from the actor's buffer (boardlaw/main.py:61-73,
+    171-181), with the ranks' shards side by side on the env axis.  Returns (chunk, remaining records)."""
+    from . import selfplay
+    from .hex import Hex
+    rec = torch.stack([r.reshape(-1, r.shape[-1]) for r in records])             # (T, world*B, R)
+    u = selfplay.unpack_records(rec, boardsize)
+    chunk = arrdict.arrdict(
+        worlds=Hex(board=u.board, seats=u.seats),
+        decisions=arrdict.arrdict(logits=u.logits, prior=u.prior, v=u.v, actions=u.actions),
+        transitions=arrdict.arrdict(rewards=u.rewards, terminal=u.terminal))
+    chunk['reward_to_go'] = reward_to_go(u.rewards.float(), u.v.float(), u.terminal, half=True)
+    n_new = (batch_size or rec.shape[1]) // rec.shape[1]
+    return chunk, records[n_new:]

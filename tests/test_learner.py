@@ -155,3 +155,46 @@ def test_optimize_updates_the_network_the_search_uses():
     assert not torch.equal(after.logits, before)
     fin = torch.isfinite(want.logits)
     assert float((after.logits.cpu()[fin] - want.logits[fin]).abs().max()) < 2e-3      # weights agree to 6e-5, not bit for bit
+
+
+@pytest.mark.gpu
+def test_actor_to_learner_round_trip():
+    """A few moves of self-play (fused engine) -> packed trajectory records (what the all-gather carries) -> chunk ->
+    one optimiser step on (t, env) samples drawn as boardlaw/main.py:170: the chunk built from the records equals the one
+    built from the actor's buffer, reward-to-go equals the oracle's on the same tensors, and the step runs."""
+    from boardlaw_b200 import arrdict, heads, learner, selfplay
+    from boardlaw_b200.hex import Hex
+    from boardlaw_b200.mcts import MCTSAgent
+    from boardlaw_b200.networks import FCModel, synthetic_state_dict
+    S, W, D, B, T = 5, 32, 2, 128, 12
+    net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(S * S), width=W, depth=D)
+    net.load_state_dict(synthetic_state_dict(S, W, D, 1))
+    agent = MCTSAgent(net.cuda(), n_nodes=16)
+    worlds = Hex.initial(B, S, device='cuda')
+    torch.manual_seed(0)
+    pool = selfplay.TrajectoryPool()
+    buffer, records = [], []
+    for _ in range(T):
+        d = agent(worlds, value=True)
+        new_worlds, tr = worlds.step(d.actions)
+        buffer.append(arrdict.arrdict(worlds=worlds, decisions=d.half(), transitions=arrdict.arrdict(
+            terminal=tr.terminal, rewards=tr.rewards.half())))
+        pool.gather(selfplay.pack_records(worlds, d, tr))
+        records.append(pool.wait())
+        worlds = new_worlds
+    chunk, rest = learner.as_chunk(buffer, B)
+    chunk2, rest2 = learner.chunk_from_records(records, S, B)
+    assert len(rest) == T - 1 and len(rest2) == T - 1
+    assert torch.equal(chunk.reward_to_go.view(torch.int16), chunk2.reward_to_go.view(torch.int16))
+    assert torch.equal(chunk.worlds.board, chunk2.worlds.board) and torch.equal(chunk.worlds.seats, chunk2.worlds.seats)
+    assert torch.equal(chunk.decisions.logits.view(torch.int16), chunk2.decisions.logits.view(torch.int16))
+    term = torch.stack([chunk.transitions.terminal.cpu()] * 2, -1)
+    want = pyref.reward_to_go(chunk.transitions.rewards.float().cpu(), chunk.decisions.v.float().cpu(), term, 1.).half()
+    assert torch.equal(chunk.reward_to_go.cpu().view(torch.int16), want.view(torch.int16))
+    assert bool(chunk.transitions.terminal.any())                                      # 12 moves of 5x5: some games ended
+    idxs = (torch.randint(T, (B,), device='cuda'), torch.arange(B, device='cuda'))
+    L = learner.Learner(agent.network, lr=1e-3)
+    out = L.optimize(chunk2[idxs])
+    assert torch.isfinite(out.policy_loss) and torch.isfinite(out.value_loss)
+    d = agent(worlds, value=True)                                                       # the search runs on the updated weights
+    assert bool(torch.isfinite(d.v).all())
