@@ -28,7 +28,7 @@ CONFIGS = {
     'c5-5': (5, 32768, 64, 256, 4), 'c5-7': (7, 32768, 64, 256, 4), 'c5-9': (9, 32768, 64, 256, 4),
     'c5-11': (11, 32768, 64, 256, 4), 'c5-13': (13, 32768, 64, 256, 4),
 }
-CPU_SAMPLE_ENVS = {'c1': 256, 'c2': 512, 'c3': 64}
+CPU_SAMPLE_ENVS = {'c1': 256, 'c2': 1024, 'c3': 64}      # ~10-20 s of host work per leg (cost is linear in envs: serial per-env loops)
 
 
 def describe(config):
