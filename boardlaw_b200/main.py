@@ -1,0 +1,44 @@
+"""The actor/learner loop of ``boardlaw/main.py:147-205`` (``run``) on the B200 path, without the reference's storage,
+statistics and live-arena side channels: decorrelate fresh worlds with random playouts, collect ``buffer_len`` moves of
+self-play, build the chunk (reward-to-go), take one optimiser step on one (t, env) sample per env, repeat.
+
+Multi-GPU (one process per GPU under ``torchrun``): every rank plays its own shard of envs; each move's trajectory records
+are all-gathered (``selfplay.TrajectoryPool``), so every rank holds the same chunk and applies the same deterministic update
+to its replica of the network — no weight broadcast is needed.
+"""
+import torch
+
+from . import arrdict, learner, learning, selfplay
+from .hex import Hex
+from .mcts import MCTSAgent
+from .networks import FCModel
+
+
+def run(boardsize, width, depth, nodes=64, c_puct=1 / 16, lr=1e-3, n_envs=32 * 1024, buffer_len=64, mix_steps=None, max_steps=1,
+        device='cuda', pool=None, seed=0, on_step=None):
+    """Returns (agent, list of arrdict(policy_loss, value_loss) per optimiser step).  ``n_envs`` is per rank; ``pool`` a
+    ``selfplay.TrajectoryPool`` when running under torch.distributed (None: single process)."""
+    torch.manual_seed(seed)
+    worlds = learning.mix(Hex.initial(n_envs, boardsize, device=device), T=2500 if mix_steps is None else mix_steps)   # main.py:150
+    network = FCModel(worlds.obs_space, worlds.action_space, width=width, depth=depth).to(worlds.device)
+    agent = MCTSAgent(network, n_nodes=nodes, c_puct=c_puct)
+    L = learner.Learner(network, lr=lr)
+    pool = pool or selfplay.TrajectoryPool()
+    world_size = pool.world
+    g = torch.Generator(device=worlds.device).manual_seed(seed)                   # same draw on every rank
+    n_all = n_envs * world_size
+    idxs = (torch.randint(buffer_len, (n_all,), device=worlds.device, generator=g), torch.arange(n_all, device=worlds.device))   # main.py:170
+    records, losses = [], []
+    for step in range(max_steps):
+        while len(records) < buffer_len:                                            # main.py:173-185
+            decisions = agent(worlds, value=True)
+            new_worlds, transition = worlds.step(decisions.actions)
+            pool.gather(selfplay.pack_records(worlds, decisions, transition))
+            records.append(pool.wait().clone())
+            worlds = new_worlds
+        chunk, records = learner.chunk_from_records(records, boardsize, n_all)    # main.py:188
+        out = L.optimize(chunk[idxs])                                              # main.py:189
+        losses.append(out)
+        if on_step is not None:
+            on_step(step, agent, out)
+    return agent, losses

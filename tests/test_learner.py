@@ -198,3 +198,15 @@ def test_actor_to_learner_round_trip():
     assert torch.isfinite(out.policy_loss) and torch.isfinite(out.value_loss)
     d = agent(worlds, value=True)                                                       # the search runs on the updated weights
     assert bool(torch.isfinite(d.v).all())
+
+
+@pytest.mark.gpu
+def test_main_run_loop():
+    """boardlaw_b200.main.run: two rounds of (8 moves of self-play -> chunk -> optimiser step) at a toy size."""
+    from boardlaw_b200 import main
+    agent, losses = main.run(boardsize=5, width=32, depth=2, nodes=8, n_envs=64, buffer_len=8, mix_steps=10, max_steps=2)
+    assert len(losses) == 2
+    for l in losses:
+        assert torch.isfinite(l.policy_loss) and torch.isfinite(l.value_loss) and float(l.policy_loss) > 0
+    # ReZero gates start at 0 (networks.py:15) and must have moved
+    assert float(dict(agent.network.named_parameters())['body.1.α'].abs()) > 0
