@@ -32,7 +32,9 @@ template <int NCH, int L>
 struct MwCfg {
     static constexpr int PS = 4 * NCH;                 // floats per row; NCH odd => eight consecutive rows start in eight different bank quartets
     static constexpr int CPL = (NCH + L - 1) / L;      // chunks per lane
-    static constexpr int KS = NCH;                     // child entries per env held in shared memory; the rest go to global scratch
+    static constexpr int KS = NCH > 31 ? 15 : NCH;     // child entries per env held in shared memory (the rest go to global scratch).  13x13: 15
+                                                       // entries buy a fourth CTA per SM (26.5 vs 29.5 ms/move at c5-13); at 11x11 the fifth CTA does
+                                                       // not pay for the spilled entries (c5-11 20.2 vs 18.9, c3 138 vs 142)
     static constexpr int ENVS = 32;                    // envs per CTA (L warps)
     static constexpr int ROWS_BYTES = ENVS * 2 * PS * 4;
     static constexpr int SMEM = ROWS_BYTES + ENVS * 16 * KS;
