@@ -399,7 +399,11 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
     static bool env_read = false;
     if (!env_read) {                                          // BL_DESCEND_VARIANT=1|2|3 overrides the default for tuning runs
         env_read = true;
-        if (const char *e = getenv("BL_DESCEND_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 3) g_descend_variant = v; }
+        if (const char *e = getenv("BL_DESCEND_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 4) g_descend_variant = v; }
+    }
+    if (g_descend_variant == 4) {
+        const int rc = bl_descend_pc(t, sim, rands, seed, bl_cu(stream));
+        if (rc != -2 && rc != -3) return rc;
     }
     if (g_descend_variant == 3 || (g_descend_variant == 0 && t->A > 81)) {
         const int rc = bl_descend_mw(t, sim, rands, seed, bl_cu(stream));
@@ -418,7 +422,7 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
 }
 
 extern "C" int bl_debug_set_descend_variant(int variant) {
-    if (variant < 0 || variant > 3) return -1;
+    if (variant < 0 || variant > 4) return -1;
     g_descend_variant = variant;
     return 0;
 }

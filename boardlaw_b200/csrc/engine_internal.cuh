@@ -60,6 +60,8 @@ int bl_descend_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed
 // descend_mw.cu: the same descent with four lanes per env (4x the warps); -3 = scratch too small, -2 = unsupported
 int bl_descend_mw(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
 int bl_mw_child_cap(const bl_tree *t);
+// descend_pc.cu: the same descent with passes and services on different warps of a CTA (variant 4); same return codes
+int bl_descend_pc(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
 int64_t bl_mw_scratch_bytes(const bl_tree *t);
 // descend.cu: expand + env step of the descents recorded in t.leaf / leaf_parent / leaf_action
 int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st);

@@ -236,6 +236,7 @@ int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint
 /* Selects the descent kernel: 0 (default) = by board size (2 up to 9x9, 3 above: measured on c2/c3/c5),
  * 2 = task-parallel descent, one lane per env with register-resident rows (descend.cu),
  * 3 = two or four lanes per env: terms split over the lanes, the S and g chains on two of them (descend_mw.cu),
+ * 4 = experimental: passes and node services on different warps of a CTA (descend_pc.cu; measured slower),
  * 1 = one lane per env in lock step, reference loops verbatim (engine.cu; kept as an on-device cross-check).
  * All produce identical results (tests/test_gpu_mcts.py runs the oracle comparison for each). */
 int bl_debug_set_descend_variant(int variant);
