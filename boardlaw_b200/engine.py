@@ -197,7 +197,7 @@ class SearchEngine:
         self.in_seats.copy_(seats)
         self.ws.counters[6:7].fill_(self.move)       # keys the in-kernel random stream of this move
         self.move += 1
-        key = (cparams.W, cparams.D, cparams.precision, float(c_puct), id(network), network._pack_key)
+        key = (cparams.W, cparams.D, cparams.precision, float(c_puct), id(network), network._pack_gen)
         if not use_graph:
             self._reset(c_puct)
             self.eval_root(cparams)

@@ -56,6 +56,7 @@ class FCModel(nn.Module):
 
         self._pack_key = None
         self._pack = None
+        self._pack_gen = 0          # bumped whenever the staged operands move to new device addresses (captured graphs key on it)
         # False routes every shape through the CUDA-core fp32 kernels (net.cu) — used as the on-device cross-check
         self.tensor_cores = True
         # tile order of the packed operands (bl_fc_params.tc_nsplit); BL_TC_NSPLIT overrides for experiments
@@ -71,7 +72,7 @@ class FCModel(nn.Module):
     def packed(self):
         """Contiguous fp32 device tensors in the order bl_fc_params wants, rebuilt when a parameter changes."""
         params = list(self.parameters())
-        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        key = (self.precision, self.tensor_cores, self.tc_nsplit) + tuple((p.data_ptr(), p._version, p.device) for p in params)
         if key != self._pack_key:
             f = lambda t: t.detach().float().contiguous()
             res = list(self.body)[1:]
@@ -90,10 +91,20 @@ class FCModel(nn.Module):
                 blob, b_head = pack_tensor_core_operands(pack, self.boardsize, self.tc_nsplit, kc=16 if W == 512 else KC, wide=W == 512)
                 pack['packed'], pack['b_head'] = blob, b_head
                 tc = dict(packed=blob.data_ptr(), b_head=b_head.data_ptr(), tc_nsplit=self.tc_nsplit)
-            cp = _lib.FCParams(
-                S=self.boardsize, W=W, D=len(res), precision=0 if self.precision == 'fp32' else 1,
-                **{k: t.data_ptr() for k, t in pack.items() if k not in ('packed', 'b_head')}, **tc)
-            self._pack, self._pack_key, self._cparams = pack, key, cp
+            if self._pack is not None and getattr(self, '_pack_cfg', None) == key[:3] and self._pack.keys() == pack.keys() and all(
+                    self._pack[k].shape == v.shape and self._pack[k].device == v.device for k, v in pack.items()):
+                # same shapes as the staged set (a weight update): refresh IN PLACE, so that the addresses baked into bl_fc_params —
+                # and into any CUDA graph captured with them — stay valid and serve the new weights
+                for k, v in pack.items():
+                    self._pack[k].copy_(v)
+                self._pack_key = key
+            else:
+                cp = _lib.FCParams(
+                    S=self.boardsize, W=W, D=len(res), precision=0 if self.precision == 'fp32' else 1,
+                    **{k: t.data_ptr() for k, t in pack.items() if k not in ('packed', 'b_head')}, **tc)
+                self._pack, self._pack_key, self._cparams = pack, key, cp
+                self._pack_cfg = key[:3]
+                self._pack_gen += 1
         return self._cparams
 
     # ---- forward --------------------------------------------------------------------------------------

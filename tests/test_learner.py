@@ -210,3 +210,39 @@ def test_main_run_loop():
         assert torch.isfinite(l.policy_loss) and torch.isfinite(l.value_loss) and float(l.policy_loss) > 0
     # ReZero gates start at 0 (networks.py:15) and must have moved
     assert float(dict(agent.network.named_parameters())['body.1.α'].abs()) > 0
+
+
+@pytest.mark.gpu
+def test_graph_replay_serves_updated_weights():
+    """The search's captured CUDA graphs hold the addresses of the staged network operands; an optimiser step writes the
+    parameters through raw pointers, so the operands are refreshed IN PLACE (same addresses): the replayed graph must
+    evaluate the updated network, not a stale or freed copy."""
+    from boardlaw_b200 import arrdict, heads, learner
+    from boardlaw_b200.hex import Hex
+    from boardlaw_b200.mcts import MCTSAgent
+    from boardlaw_b200.networks import FCModel, synthetic_state_dict
+    S, W, D, N = 5, 32, 2, 256
+    w, tl, tv = _batch(S, N, 31)
+    net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(S * S), width=W, depth=D)
+    net.load_state_dict(synthetic_state_dict(S, W, D, 8))
+    net = net.cuda()
+    worlds = Hex(board=w.board.cuda(), seats=w.seats.cuda())
+    agent = MCTSAgent(net, n_nodes=8, noise_eps=0.)
+    torch.manual_seed(0)
+    d0 = agent(worlds)                      # captures the graphs
+    agent(worlds)                           # replays them
+    gen = net._pack_gen
+    L = learner.Learner(net, lr=1e-2)
+    batch = arrdict.arrdict(worlds=worlds, decisions=arrdict.arrdict(logits=tl.cuda()), reward_to_go=tv.cuda())
+    for _ in range(3):
+        L.optimize(batch)
+        junk = torch.full((1 << 22,), float('nan'), device='cuda')          # anything freed by the update gets overwritten
+        d1 = agent(worlds)
+        del junk
+        want = net(worlds).logits           # eager forward with the current weights
+        assert net._pack_gen == gen + 1     # re-pointing the parameters into the flat buffer restaged once; the updates did not
+        assert bool(torch.isfinite(d1.v).all())
+        fin = torch.isfinite(want)
+        assert torch.equal(torch.isfinite(d1.prior), fin)
+        assert float((d1.prior.float()[fin] - want[fin]).abs().max()) < 4e-3      # prior = half(log(exp(logits))) of the root evaluation
+    assert float((d1.prior.float()[fin] - d0.prior.float()[fin]).abs().max()) > 1e-2
