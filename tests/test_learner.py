@@ -240,7 +240,7 @@ def test_graph_replay_serves_updated_weights():
         d1 = agent(worlds)
         del junk
         want = net(worlds).logits           # eager forward with the current weights
-        assert net._pack_gen == gen + 1     # re-pointing the parameters into the flat buffer restaged once; the updates did not
+        assert net._pack_gen == gen         # same shapes: refreshed in place, the staged operands never moved
         assert bool(torch.isfinite(d1.v).all())
         fin = torch.isfinite(want)
         assert torch.equal(torch.isfinite(d1.prior), fin)
