@@ -243,15 +243,19 @@ def run_ours(args):
     h2d = hb.numel() * hb.element_size() + hs.numel() * hs.element_size()
     d2h = sum(v.numel() * v.element_size() for v in out.values())
 
+    io = {'hb': hb, 'hs': hs}
+
     def e2e_step():
-        w = Hex(board=hb.to(device, non_blocking=True), seats=hs.to(device, non_blocking=True))
+        w = Hex(board=io['hb'].to(device, non_blocking=True), seats=io['hs'].to(device, non_blocking=True))
         d = agent(w)
         w2, tr = w.step(d.actions)
         for k, src in (('actions', d.actions), ('logits', d.logits), ('v', d.v), ('board', w2.board), ('seats', w2.seats),
                        ('rewards', tr.rewards), ('terminal', tr.terminal)):
             out[k].copy_(src, non_blocking=True)
         torch.cuda.current_stream().synchronize()            # the caller reads the result on the host
-        hb.copy_(out['board']); hs.copy_(out['seats'])        # next step's inputs come from the host again
+        # next step's inputs come from the host again: the pinned result buffers become the next inputs (no host-side memcpy)
+        io['hb'], out['board'] = out['board'], io['hb']
+        io['hs'], out['seats'] = out['seats'], io['hs']
 
     e2e_step()
     barrier()
