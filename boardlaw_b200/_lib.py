@@ -13,7 +13,7 @@ import torch
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / 'libboardlaw_b200.so'
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class FCParams(Structure):
@@ -59,6 +59,8 @@ SIGNATURES = {
     'bl_tree_backup': (c_int, [POINTER(Tree), c_int, P]),
     'bl_debug_set_descend_variant': (c_int, [c_int]),
     'bl_debug_set_phase_profile': (c_int, [P]),
+    'bl_debug_set_fx_trace': (c_int, [P]),
+    'bl_debug_set_descend_grid': (c_int, [c_int]),
     'bl_selftest_division': (c_int, [c_uint64, c_int, c_int, P, P]),
     'bl_tree_eval_scratch_bytes': (c_int64, [POINTER(Tree), POINTER(FCParams)]),
     'bl_tree_eval_leaves': (c_int, [POINTER(Tree), POINTER(FCParams), c_int, P, P]),

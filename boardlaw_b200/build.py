@@ -27,6 +27,7 @@ SOURCES = {
     'engine.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
     'descend.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'] + (['-DBL_CHILD_ILP=' + os.environ['BL_CHILD_ILP']] if 'BL_CHILD_ILP' in os.environ else []),
     'descend_mw.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
+    'descend_fx.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
     'descend_pc.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
     'net.cu': [],
     'net_tc.cu': [],

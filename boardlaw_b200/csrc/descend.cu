@@ -553,6 +553,12 @@ extern "C" int bl_debug_set_phase_profile(uint64_t *buf) {
     return 0;
 }
 
+extern "C" int bl_debug_set_descend_grid(int warps) {
+    read_gate_env();
+    g_grid_limit = warps > 0 ? warps : 0;
+    return 0;
+}
+
 extern "C" int bl_selftest_division(uint64_t seed, int n_div, int n_num, uint64_t *mismatch, bl_stream stream) {
     divtest_kernel<<<BL_NUM_SMS * 8, 256, 0, bl_cu(stream)>>>(seed, n_div, n_num, reinterpret_cast<unsigned long long *>(mismatch));
     BL_LAUNCH_CHECK();

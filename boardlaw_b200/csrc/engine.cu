@@ -24,7 +24,8 @@ constexpr int FP = ENT + 1;        // float column pitch (odd: conflict-free for
 constexpr int BPITCH = ENT + 4;    // byte column pitch (17 words: consecutive cells land on distinct banks)
 
 // counters slots
-int g_descend_variant = 0;      // 0 = by board size (measured): A <= 81 one lane per env (descend.cu), larger boards four lanes (descend_mw.cu)
+int g_descend_variant = 0;      // 0 = the certified fast descent (descend_fx.cu) where the shape allows, else by board size: A <= 81 one
+                                // lane per env (descend.cu), larger boards four lanes (descend_mw.cu)
 
 __global__ void __launch_bounds__(256) reset_kernel(bl_tree t, const uint8_t *__restrict__ board,
                                                     const int32_t *__restrict__ seats, bl_half c_puct) {
@@ -399,7 +400,11 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
     static bool env_read = false;
     if (!env_read) {                                          // BL_DESCEND_VARIANT=1|2|3 overrides the default for tuning runs
         env_read = true;
-        if (const char *e = getenv("BL_DESCEND_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 4) g_descend_variant = v; }
+        if (const char *e = getenv("BL_DESCEND_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 5) g_descend_variant = v; }
+    }
+    if (g_descend_variant == 5 || g_descend_variant == 0) {
+        const int rc = bl_descend_fx(t, sim, rands, seed, bl_cu(stream));
+        if (rc != -2) return rc;                             // unsupported shape: the exact kernels take it
     }
     if (g_descend_variant == 4) {
         const int rc = bl_descend_pc(t, sim, rands, seed, bl_cu(stream));
@@ -422,7 +427,7 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
 }
 
 extern "C" int bl_debug_set_descend_variant(int variant) {
-    if (variant < 0 || variant > 4) return -1;
+    if (variant < 0 || variant > 5) return -1;
     g_descend_variant = variant;
     return 0;
 }

@@ -3,7 +3,10 @@
 #include "common.cuh"
 
 // bl_tree.counters slots
-enum { C_EVALS = 0, C_CHILDREN = 1, C_ITERS = 2, C_DESCENTS = 3, C_BACKUP_NODES = 4, C_ERRORS = 5, C_MOVE = 6, C_QUEUE = 7 };
+enum { C_EVALS = 0, C_CHILDREN = 1, C_ITERS = 2, C_DESCENTS = 3, C_BACKUP_NODES = 4, C_ERRORS = 5, C_MOVE = 6, C_QUEUE = 7,
+       // certified fast descent (descend_fx.cu): evaluations sent to the exact path because the stop test / the sampled action / a
+       // guard (doubt too large, tiny values) could not be certified, and exact passes run there
+       C_FLAG_STOP = 8, C_FLAG_SAMPLE = 9, C_FLAG_OTHER = 10, C_EXACT_PASSES = 11 };
 
 static_assert(sizeof(bl_node) == 16 && sizeof(bl_aux) == 16, "tree records are 16 bytes");
 
@@ -63,6 +66,9 @@ int bl_mw_child_cap(const bl_tree *t);
 // descend_pc.cu: the same descent with passes and services on different warps of a CTA (variant 4); same return codes
 int bl_descend_pc(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
 int64_t bl_mw_scratch_bytes(const bl_tree *t);
+// descend_fx.cu: certified fast descent (variant 5): closed-form sums over the children, decisions certified against an error
+// bound, exact path otherwise; followed by expand + env step.  -2 = unsupported shape
+int bl_descend_fx(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
 // descend.cu: expand + env step of the descents recorded in t.leaf / leaf_parent / leaf_action
 int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st);
 // descend.cu: device buffer of the optional phase clock (NULL = off); slots 0..15 descent, 16..31 network

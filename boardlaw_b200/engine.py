@@ -43,7 +43,7 @@ class SearchEngine:
             c_puct=z((B,), torch.float16),
             leaf=z((B,), torch.int16), leaf_parent=z((B,), torch.int16), leaf_action=z((B,), torch.int16),
             leaf_v=z((B, Sn), torch.float16),
-            prior=z((B, A), torch.float16), qrange=z((T + 1, 2), torch.float32), counters=z((8,), torch.int64))
+            prior=z((B, A), torch.float16), qrange=z((T + 1, 2), torch.float32), counters=z((16,), torch.int64))
         if mirror_logits:
             self.ws['logits'] = torch.full((B, T, A), np.nan, dtype=torch.float16, device=dev)
         views = arrdict.arrdict(

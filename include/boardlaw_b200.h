@@ -206,7 +206,9 @@ typedef struct bl_tree {
                              chase leaf -> aux)                                                                       */
     bl_half *prior;       /* (B,A)  half: the (noised) root logits as stored, = decisions.logits[:,0]       */
     float *qrange;        /* (T+1,2) per-simulation (min,max) of w/(n+1e-4), ordered-int encoded    */
-    uint64_t *counters;   /* (8,) policy evals, children seen, newton iters, descents, backup nodes, errors, move, queue */
+    uint64_t *counters;   /* (16,) policy evals, children seen, newton iters, descents, backup nodes, errors, move, queue; certified fast
+                             descent: [8] evaluations whose stop test, [9] sampled action, [10] guards could not be certified (exact path),
+                             [11] exact passes run */
     const float *exp_lut; /* (65536,)                                                               */
     void *scratch;        /* device scratch for the descent's per-lane child lists                          */
     int64_t scratch_bytes;/* >= bl_tree_scratch_bytes(t)                                                    */
@@ -233,13 +235,24 @@ int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, const void 
 int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed,
                            bl_stream stream);
 
-/* Selects the descent kernel: 0 (default) = by board size (2 up to 9x9, 3 above: measured on c2/c3/c5),
+/* Selects the descent kernel: 0 (default) = 5 where the shape allows (A <= 255, T <= 256), else by board size (2 up to 9x9, 3 above),
+ * 5 = certified fast descent (descend_fx.cu): closed-form sums over the children only, every decision certified against a
+ *     rigorous bound on |reference - ours| and recomputed with the reference's arithmetic when the bound does not separate it,
  * 2 = task-parallel descent, one lane per env with register-resident rows (descend.cu),
  * 3 = two or four lanes per env: terms split over the lanes, the S and g chains on two of them (descend_mw.cu),
  * 4 = experimental: passes and node services on different warps of a CTA (descend_pc.cu; measured slower),
  * 1 = one lane per env in lock step, reference loops verbatim (engine.cu; kept as an on-device cross-check).
  * All produce identical results (tests/test_gpu_mcts.py runs the oracle comparison for each). */
 int bl_debug_set_descend_variant(int variant);
+
+/* Caps the number of warps of the one-lane descent (variant 2): with fewer lanes than envs the lanes pull envs from a global
+ * queue (the path large batches take when not every env fits on the device at once).  0 = no cap.  For tests and tuning. */
+int bl_debug_set_descend_grid(int warps);
+
+/* Trace of the certified fast descent (variant 5): when `buf` (B x 64 floats on the device) is non-NULL every env's LAST policy
+ * evaluation of a launch leaves [4k..4k+3] = (alpha, S-1, bound, alpha doubt) of Newton pass k < 8 and [32..39] = (final alpha,
+ * sampling bound, flag, passes, doubt, S, |g|, action).  NULL (default) switches it off. */
+int bl_debug_set_fx_trace(float *buf);
 
 /* Phase clock of the descent and network kernels: when `buf` (32 x uint64 on the device, zeroed by the caller) is non-NULL every warp adds the
  * cycles it spent per phase — [0] loop head, [1] sample+advance, [2] finish/fetch, [3] visit, [4] child terms, [5] pass,
