@@ -13,7 +13,7 @@ import torch
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / 'libboardlaw_b200.so'
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class FCParams(Structure):
@@ -27,7 +27,7 @@ class FCParams(Structure):
 class Tree(Structure):
     """``bl_tree`` (include/boardlaw_b200.h)."""
     _fields_ = [('B', c_int), ('T', c_int), ('S', c_int), ('A', c_int), ('Sn', c_int), ('AP', c_int), ('BP', c_int),
-                ('pi', c_void_p), ('logits', c_void_p), ('board', c_void_p), ('node', c_void_p), ('aux', c_void_p), ('parent_of', c_void_p), ('kids', c_void_p),
+                ('pi', c_void_p), ('cpi', c_void_p), ('psum', c_void_p), ('cprior', c_void_p), ('logits', c_void_p), ('board', c_void_p), ('node', c_void_p), ('aux', c_void_p), ('parent_of', c_void_p), ('kids', c_void_p),
                 ('c_puct', c_void_p), ('leaf', c_void_p),
                 ('leaf_parent', c_void_p), ('leaf_action', c_void_p), ('leaf_v', c_void_p), ('prior', c_void_p), ('qrange', c_void_p),
                 ('counters', c_void_p), ('exp_lut', c_void_p), ('scratch', c_void_p), ('scratch_bytes', c_int64)]
@@ -59,7 +59,6 @@ SIGNATURES = {
     'bl_tree_backup': (c_int, [POINTER(Tree), c_int, P]),
     'bl_debug_set_descend_variant': (c_int, [c_int]),
     'bl_debug_set_phase_profile': (c_int, [P]),
-    'bl_debug_set_fx_trace': (c_int, [P]),
     'bl_debug_set_descend_grid': (c_int, [c_int]),
     'bl_selftest_division': (c_int, [c_uint64, c_int, c_int, P, P]),
     'bl_tree_eval_scratch_bytes': (c_int64, [POINTER(Tree), POINTER(FCParams)]),

@@ -52,6 +52,7 @@ __device__ __forceinline__ void bl_expand_one(const bl_tree &t, int sim, int b, 
         t.node[node0 + parent].first_child = (int16_t)sim;
         t.parent_of[(size_t)b * ((T + 7) & ~7) + sim] = (int16_t)parent;
         t.kids[(node0 + parent) * ((T + 63) >> 6) + (sim >> 6)] |= 1ull << (sim & 63);
+        if (t.cprior) t.cprior[node0 + sim] = t.pi[(node0 + parent) * t.AP + action];
         t.leaf[b] = (int16_t)leaf;
     } else {                                                    // stopped at an existing terminal child: reuse its slot
         ln = bl_ld_node(t.node + node0 + leaf);

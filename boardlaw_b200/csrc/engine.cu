@@ -24,8 +24,7 @@ constexpr int FP = ENT + 1;        // float column pitch (odd: conflict-free for
 constexpr int BPITCH = ENT + 4;    // byte column pitch (17 words: consecutive cells land on distinct banks)
 
 // counters slots
-int g_descend_variant = 0;      // 0 = the certified fast descent (descend_fx.cu) where the shape allows, else by board size: A <= 81 one
-                                // lane per env (descend.cu), larger boards four lanes (descend_mw.cu)
+int g_descend_variant = 0;      // 0 = by board size (measured): A <= 81 one lane per env (descend.cu), larger boards four lanes (descend_mw.cu)
 
 __global__ void __launch_bounds__(256) reset_kernel(bl_tree t, const uint8_t *__restrict__ board,
                                                     const int32_t *__restrict__ seats, bl_half c_puct) {
@@ -66,17 +65,35 @@ __global__ void __launch_bounds__(256) set_eval_kernel(bl_tree t, int node, cons
         const int nd = node >= 0 ? node : t.leaf[b];
         if (nd < 0) continue;
         const size_t slot = (size_t)b * t.T + nd;
-        float mx = 0.f, mn = BL_INF;
+        float mx = 0.f, mn = BL_INF, pa = 0.f;
         int fz = 255, lz = -1;
-        for (int a = lane; a < t.A; a += 32) {
-            const size_t i = (size_t)b * t.A + a;
-            const bl_half h = HALF_IN ? reinterpret_cast<const bl_half *>(logits_)[i] : bl_f2h(reinterpret_cast<const float *>(logits_)[i]);
-            const float p = t.exp_lut[h];
-            t.pi[slot * t.AP + a] = p;
-            if (nd == 0) t.prior[i] = h;
-            if (t.logits) t.logits[slot * t.A + a] = h;
-            if (p != 0.f) { mx = fmaxf(mx, p); mn = fminf(mn, p); fz = min(fz, a); lz = max(lz, a); }
+        double carry = 0.;                                     // running prefix sum of the row (cpi), chunk of 32 actions at a time
+        for (int a0 = 0; a0 < t.AP; a0 += 32) {
+            const int a = a0 + lane;
+            float p = 0.f;
+            if (a < t.A) {
+                const size_t i = (size_t)b * t.A + a;
+                const bl_half h = HALF_IN ? reinterpret_cast<const bl_half *>(logits_)[i] : bl_f2h(reinterpret_cast<const float *>(logits_)[i]);
+                p = t.exp_lut[h];
+                t.pi[slot * t.AP + a] = p;
+                if (nd == 0) t.prior[i] = h;
+                if (t.logits) t.logits[slot * t.A + a] = h;
+                if (p != 0.f) { mx = fmaxf(mx, p); mn = fminf(mn, p); fz = min(fz, a); lz = max(lz, a); }
+                pa = __fmaf_rn((float)a, p, pa);
+            }
+            double run = (double)p;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, run, o);
+                if (lane >= o) run += up;
+            }
+            run += carry;
+            if (t.cpi && a < t.AP) t.cpi[slot * t.AP + a] = (float)run;
+            carry = __shfl_sync(0xffffffffu, run, 31);
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) pa += __shfl_xor_sync(0xffffffffu, pa, o);
+        if (t.cpi && lane == 0) t.psum[slot] = pa;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -402,9 +419,9 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
         env_read = true;
         if (const char *e = getenv("BL_DESCEND_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 5) g_descend_variant = v; }
     }
-    if (g_descend_variant == 5 || g_descend_variant == 0) {
+    if (g_descend_variant == 5 && t->cpi) {
         const int rc = bl_descend_fx(t, sim, rands, seed, bl_cu(stream));
-        if (rc != -2) return rc;                             // unsupported shape: the exact kernels take it
+        if (rc != -2 && rc != -3) return rc;                 // unsupported shape / scratch: the exact kernels take it
     }
     if (g_descend_variant == 4) {
         const int rc = bl_descend_pc(t, sim, rands, seed, bl_cu(stream));

@@ -69,6 +69,7 @@ int64_t bl_mw_scratch_bytes(const bl_tree *t);
 // descend_fx.cu: certified fast descent (variant 5): closed-form sums over the children, decisions certified against an error
 // bound, exact path otherwise; followed by expand + env step.  -2 = unsupported shape
 int bl_descend_fx(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
+int64_t bl_fx_scratch_bytes(const bl_tree *t);
 // descend.cu: expand + env step of the descents recorded in t.leaf / leaf_parent / leaf_action
 int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st);
 // descend.cu: device buffer of the optional phase clock (NULL = off); slots 0..15 descent, 16..31 network

@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
             // bl_tree_set_eval does for injected evaluations); otherwise fp32 logits / v for the caller
             const int nd = sv >> 8;
             const size_t slot = p.tree_mode && live ? (size_t)m * p.tree.T + nd : 0;
-            float pmax = 0.f, pmin = BL_INF_F;
+            float pmax = 0.f, pmin = BL_INF_F, pa = 0.f;
+            double prun = 0.;                                      // running sum of the pi row -> cpi (prefix sums, rounded once per entry)
             int fz = 255, lz = -1;
             for (int u = 0; u < nu; u++) {
                 float y[16];
@@ -447,6 +448,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                         for (int j = 0; j < 16; j += 4)
                             if (u * 16 + j < p.tree.AP)
                                 *reinterpret_cast<float4 *>(p.tree.pi + slot * p.tree.AP + u * 16 + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
+                        if (p.tree.cpi) {                          // prefix sums of the row for the certified fast descent (variant 5)
+                            float cp[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                prun += (double)pv[j];
+                                cp[j] = (float)prun;
+                                pa = __fmaf_rn((float)(u * 16 + j), pv[j], pa);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                if (u * 16 + j < p.tree.AP)
+                                    *reinterpret_cast<float4 *>(p.tree.cpi + slot * p.tree.AP + u * 16 + j) = make_float4(cp[j], cp[j + 1], cp[j + 2], cp[j + 3]);
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; j++)
@@ -461,6 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fc_tc_kernel(const __grid_const
                     uint32_t *ax = reinterpret_cast<uint32_t *>(p.tree.aux + slot);
                     ax[1] = (uint32_t)bl_f2h(v0) | ((uint32_t)bl_f2h(v1) << 16);
                     reinterpret_cast<uint32_t *>(p.tree.leaf_v)[m] = ax[1];
+                    if (p.tree.cpi) p.tree.psum[slot] = pa;
                     reinterpret_cast<uint2 *>(ax)[1] = make_uint2(__float_as_uint(pmax), (__float_as_uint(pmin) >> 16) | ((uint32_t)(fz & 255) << 16) |
                                                                                                ((uint32_t)((lz < 0 ? 0 : lz) & 255) << 24));
                 } else {

@@ -7,6 +7,7 @@ work is three launches per simulation (descend+expand+step, network, backup+q-ra
 graph after the first move.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -21,7 +22,7 @@ def _round_up(x, m):
 
 class SearchEngine:
 
-    def __init__(self, n_envs, boardsize, n_nodes, device, mirror_logits=False, seed=0):
+    def __init__(self, n_envs, boardsize, n_nodes, device, mirror_logits=False, seed=0, fast_descent=None):
         self.B, self.S, self.T = n_envs, boardsize, n_nodes
         self.A, self.Sn = boardsize * boardsize, 2
         self.AP, self.BP = _round_up(self.A, 4), _round_up(self.A, 16)
@@ -44,6 +45,11 @@ class SearchEngine:
             leaf=z((B,), torch.int16), leaf_parent=z((B,), torch.int16), leaf_action=z((B,), torch.int16),
             leaf_v=z((B, Sn), torch.float16),
             prior=z((B, A), torch.float16), qrange=z((T + 1, 2), torch.float32), counters=z((16,), torch.int64))
+        # the certified fast descent (variant 5) samples from the prefix sums of the pi rows: three more arrays
+        if fast_descent is None:
+            fast_descent = os.environ.get('BL_DESCEND_VARIANT') == '5'
+        if fast_descent:
+            self.ws.update(cpi=z((B, T, self.AP), torch.float32), psum=z((B, T), torch.float32), cprior=z((B, T), torch.float32))
         if mirror_logits:
             self.ws['logits'] = torch.full((B, T, A), np.nan, dtype=torch.float16, device=dev)
         views = arrdict.arrdict(
@@ -54,7 +60,8 @@ class SearchEngine:
         self.exp_lut = _lib.exp_lut(dev)
         self.log_lut = _lib.log_lut(dev)
         fields = {k: self.ws[k].data_ptr() for k in self.ws}
-        fields.setdefault('logits', None)
+        for k in ('logits', 'cpi', 'psum', 'cprior'):
+            fields.setdefault(k, None)
         self.ctree = _lib.Tree(B=B, T=T, S=self.S, A=A, Sn=Sn, AP=self.AP, BP=self.BP, exp_lut=self.exp_lut.data_ptr(),
                                 scratch=None, scratch_bytes=0, **fields)
         nscratch = int(_lib.lib().bl_tree_scratch_bytes(ctypes.byref(self.ctree)))

@@ -190,6 +190,11 @@ typedef struct bl_tree {
     int AP;               /* row pitch of pi in floats (A rounded up to a multiple of 4)            */
     int BP;               /* row pitch of board in bytes (A rounded up to a multiple of 16)         */
     float *pi;            /* (B,T,AP) exp(logits) as fp32, value of exp_lut[half(logit)]; pad = 0    */
+    float *cpi;           /* NULL, or (with psum and cprior; needed by descent variant 5 only) (B,T,AP) inclusive prefix sums of the pi row (accumulated in double, rounded once per entry; pad = total):
+                             what the certified fast descent samples from (binary search) and takes the row's mass from              */
+    float *psum;          /* (B,T)  sum_a a*pi[a] per node (fp32; feeds only the descent's error bound)                              */
+    float *cprior;        /* (B,T)  pi[parent][relation] of each node: its prior under its parent, copied by the expand step so that a
+                             visit needs no access to the parent's pi row for its children                                           */
     bl_half *logits;      /* (B,T,A) half or NULL: reference-layout mirror (kept only in debug mode) */
     uint8_t *board;       /* (B,T,BP) u8 absolute-frame boards                                      */
     bl_node *node;        /* (B,T)                                                                  */
@@ -235,9 +240,10 @@ int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, const void 
 int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed,
                            bl_stream stream);
 
-/* Selects the descent kernel: 0 (default) = 5 where the shape allows (A <= 255, T <= 256), else by board size (2 up to 9x9, 3 above),
- * 5 = certified fast descent (descend_fx.cu): closed-form sums over the children only, every decision certified against a
- *     rigorous bound on |reference - ours| and recomputed with the reference's arithmetic when the bound does not separate it,
+/* Selects the descent kernel: 0 (default) = by board size (2 up to 9x9, 3 above: measured on c2/c3/c5),
+ * 5 = certified fast descent (descend_fx.cu; needs t->cpi / psum / cprior, A <= 255, T <= 256): closed-form sums over the children
+ *     only, every decision certified against a rigorous bound on |reference - ours| and recomputed with the reference's arithmetic
+ *     when the bound does not separate it (bit-identical results, fewer instructions, but not faster: DESIGN.md 5.1c),
  * 2 = task-parallel descent, one lane per env with register-resident rows (descend.cu),
  * 3 = two or four lanes per env: terms split over the lanes, the S and g chains on two of them (descend_mw.cu),
  * 4 = experimental: passes and node services on different warps of a CTA (descend_pc.cu; measured slower),
@@ -249,10 +255,6 @@ int bl_debug_set_descend_variant(int variant);
  * queue (the path large batches take when not every env fits on the device at once).  0 = no cap.  For tests and tuning. */
 int bl_debug_set_descend_grid(int warps);
 
-/* Trace of the certified fast descent (variant 5): when `buf` (B x 64 floats on the device) is non-NULL every env's LAST policy
- * evaluation of a launch leaves [4k..4k+3] = (alpha, S-1, bound, alpha doubt) of Newton pass k < 8 and [32..39] = (final alpha,
- * sampling bound, flag, passes, doubt, S, |g|, action).  NULL (default) switches it off. */
-int bl_debug_set_fx_trace(float *buf);
 
 /* Phase clock of the descent and network kernels: when `buf` (32 x uint64 on the device, zeroed by the caller) is non-NULL every warp adds the
  * cycles it spent per phase — [0] loop head, [1] sample+advance, [2] finish/fetch, [3] visit, [4] child terms, [5] pass,

@@ -41,6 +41,9 @@ class Stats:
         self.iters = 0
         self.children = 0
         self.delta_sum = 0.
+        self.resolved = self.resolve_passes = self.bad_resolved = 0
+        self.resolve_hist = [0] * 10
+        self.resolve_budget = 1 << 30
 
     def report(self):
         n = max(self.evals, 1)
@@ -50,6 +53,8 @@ class Stats:
         print(f'certified but different: stop {self.bad_stop}, action {self.bad_action}  (must be 0)')
         print(f'largest observed deviation / bound: S-1 {self.max_ne_ratio:.3f}, prefix sums {self.max_cum_ratio:.3f}, alpha {self.max_alpha_ratio:.3f}')
         print(f'mean sampling bound delta {self.delta_sum / n:.3e}')
+        print(f'flagged evaluations resolved by the kernel\'s control flow (eval_one): {self.resolved}, exact passes {self.resolve_passes} '
+              f'({self.resolve_passes / max(self.resolved, 1):.2f} per flagged evaluation, histogram {self.resolve_hist}), wrong {self.bad_resolved} (must be 0)')
 
 
 def exact_eval(pi, q, lam, r, trace=12):
@@ -228,6 +233,15 @@ def replay_descend(logits, q, n, c_puct, seats, terminal, children, rands, stats
         stats.children += int(child.sum())
         stats.flag_stop += int((flag == 1).sum()); stats.flag_sample += int((flag == 2).sum())
         stats.flag_guard += int((flag == 3).sum()); stats.flag_tiny += int((flag == 4).sum())
+        for i in np.nonzero(flag != 0)[0][:stats.resolve_budget]:
+            a1, it1, xp = eval_one(pi[i], qa[i], child[i], lam[i], r[i])
+            stats.resolved += 1
+            stats.resolve_passes += xp
+            stats.resolve_hist[min(xp, 9)] += 1
+            stats.bad_resolved += int(a1 != act[i]) + int(it1 != iters[i])
+        for i in np.nonzero(flag == 0)[0][:2]:                               # and a couple of unflagged ones: same answer, no exact pass
+            a1, it1, xp = eval_one(pi[i], qa[i], child[i], lam[i], r[i])
+            stats.bad_resolved += int(a1 != act[i]) + int(it1 != iters[i])
         ok = flag == 0
         stats.bad_stop += int((ok & (fiters != iters)).sum())
         stats.bad_action += int((ok & (fact != act)).sum())
@@ -265,3 +279,139 @@ def _exp_lut():
         import oracle
         _lut = oracle.exp_table()
     return _lut
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# the kernel's complete control flow for ONE evaluation (scalar): fast Newton with a safe point, exact passes on demand
+# ------------------------------------------------------------------------------------------------------------------------
+def _exact_pass(top, q, alpha):
+    """One pass of the reference's loops at alpha: (S, g, prefix sums, terms) in fp32, sequential order."""
+    A = len(top)
+    S = f32(0); g = f32(0)
+    cum = np.zeros(A, f32); terms = np.zeros(A, f32)
+    with np.errstate(all='ignore'):
+        for a in range(A):
+            bot = f32(alpha - q[a])
+            p = f32(top[a] / bot)
+            S = f32(S + p)
+            g = f32(g + f32(f32(-top[a]) / f32(bot * bot)))
+            cum[a] = S; terms[a] = p
+    return S, g, cum, terms
+
+
+def _exact_sample(terms, cum, r):
+    action, valid = -1, -1
+    for a in range(len(terms)):
+        if terms[a] > 0:
+            if cum[a] >= r:
+                return a
+            valid = a
+    return valid
+
+
+def _all_exact(top, q, alpha0, r):
+    """The reference's loops verbatim (newton_search + sampling), one exact pass per Newton pass."""
+    alpha, it, ne_prev, xp = alpha0, 0, f32(np.inf), 0
+    with np.errstate(all='ignore'):
+        while True:
+            xS, xg, cum, terms = _exact_pass(top, q, alpha)
+            xp += 1; it += 1
+            ne = f32(xS - f32(1))
+            if it > 100 or ne < f32(1e-3) or ne_prev == ne:
+                return _exact_sample(terms, cum, r), min(it, 100), xp
+            alpha = f32(alpha - f32(ne / xg)); ne_prev = ne
+
+
+def eval_one(pi, q, child, lam, r):
+    """Returns (action, newton passes as the reference counts them, exact passes used).  pi, q (A,) f32, child (A,) bool."""
+    A = len(pi)
+    top = (lam * pi).astype(f32)
+    nz = top > 0
+    if not nz.any():
+        return -1, 0, 0
+    first_nz, last_nz = int(nz.argmax()), int(A - 1 - nz[::-1].argmax())
+    alpha0 = f32(np.max(q + np.maximum(top, f32(1e-4))))
+    wgt = np.maximum(last_nz + 1 - np.arange(A), 0).astype(np.float64)
+    pi_cl = np.where(child, 0, pi).astype(np.float64)
+    # (the kernel: M = lambda*P_all - sum t_c in double; same quantity up to u)
+    M = f32(lam * pi_cl.sum()); MW = f32(lam * (pi_cl * wgt).sum())
+    cidx = np.nonzero(child)[0]
+    nc = len(cidx)
+    cours = f32(nc + 13) * U
+    qmax = f32(q[cidx].max()) if nc else f32(0)
+    if np.where(nz, top, np.inf).min() < TINY:
+        return _all_exact(top, q, alpha0, r)
+    xpasses = 0
+    alpha, e, it = alpha0, f32(0), 0
+    ne_prev, D_prev = f32(np.inf), f32(0)
+    safe = (alpha, it, ne_prev, D_prev)
+    with np.errstate(all='ignore'):
+        while True:
+            # ---- fast Newton until a decision or a doubt
+            stopped = False
+            while True:
+                if e == 0:
+                    safe = (alpha, it, ne_prev, D_prev)
+                ra = f32(f32(1) / alpha)
+                S = f32(M * ra); G = f32(S * ra); H = f32(G * ra)
+                ES = f32(MW * ra); EG = f32(ES * ra)
+                for a in cidx:
+                    rc = f32(f32(1) / f32(alpha - q[a]))
+                    s = f32(top[a] * rc); g = f32(s * rc)
+                    S = f32(S + s); G = f32(G + g); H = f32(H + f32(g * rc))
+                    ES = f32(ES + f32(wgt[a]) * s); EG = f32(EG + f32(wgt[a]) * g)
+                H = f32(2) * H
+                ESn = f32(U * f32(1.01) * ES + (f32(2) * U + cours) * S)
+                EGn = f32(U * f32(1.01) * EG + (f32(4) * U + cours) * G)
+                ne = f32(S - f32(1))
+                Dk = f32(ESn + G * e * f32(1.05) + f32(2) * U * abs(ne))
+                it += 1
+                guard_ok = (e <= GUARD * (alpha - qmax)) and np.isfinite(S) and np.isfinite(G) and G > 0 and it <= MAX_FAST_ITERS
+                if not guard_ok:
+                    a1, i1, xp = _all_exact(top, q, alpha0, r)
+                    return a1, i1, xp + xpasses
+                if ne < f32(1e-3) - Dk:
+                    stopped = True; break
+                if not ((ne > f32(1e-3) + Dk) and (abs(ne - ne_prev) > Dk + D_prev)):
+                    break
+                rG = f32(1) / G
+                L = f32(1.2) * (max(ne, f32(0)) + f32(2) * G * e) * H * rG * rG
+                R = f32(1.05) * (Dk * rG + abs(ne) * rG * (EGn * rG + f32(4) * U))
+                eps = f32(L * e + R)
+                step = f32(ne / G)
+                a_new = f32(alpha + step)
+                err = f32(step - f32(a_new - alpha))
+                ab = np.float32(abs(a_new)).view(np.uint32)
+                ulp = (ab & np.uint32(0x7f800000)).view(f32) * f32(2.0 ** -23)
+                exact = (eps < f32(0.5) * ulp - abs(err)) and (ab & np.uint32(0x007fffff)) != 0 and abs(step) <= abs(alpha)
+                e = f32(0) if exact else f32(eps + ulp)
+                alpha = a_new; ne_prev = ne; D_prev = Dk
+            if stopped:
+                # ---- certified sampling
+                if r <= 0:
+                    return first_nz, it, xpasses
+                ra = f32(f32(1) / alpha); k = f32(lam * ra)
+                p = np.where(child, 0, k.astype(np.float64) * pi.astype(np.float64))
+                for a in cidx:
+                    p[a] = f32(top[a] * f32(f32(1) / f32(alpha - q[a])))
+                cum = np.cumsum(p)
+                delta = f32(ESn + G * e * f32(1.05))
+                lo_n = int((cum < float(r) - float(delta)).sum()); hi_n = int((cum <= float(r) + float(delta)).sum())
+                if lo_n == hi_n:
+                    return (lo_n if lo_n < A else last_nz), it, xpasses
+            # ---- a doubt: one exact pass at the safe point (the last iterate known to be the reference's float)
+            alpha, it, ne_prev, D_prev = safe
+            xS, xg, cum, terms = _exact_pass(top, q, alpha)
+            xpasses += 1
+            it += 1
+            ne = f32(xS - f32(1))
+            if ne < f32(1e-3):
+                return _exact_sample(terms, cum, r), it, xpasses
+            # `error == new_error`: error is the reference's previous S-1, known exactly when D_prev == 0 and to D_prev otherwise
+            if (D_prev == 0 and ne_prev == ne):
+                return _exact_sample(terms, cum, r), it, xpasses
+            if D_prev != 0 and not (abs(ne - ne_prev) > D_prev):
+                a1, i1, xp = _all_exact(top, q, alpha0, r)
+                return a1, i1, xp + xpasses
+            alpha = f32(alpha - f32(ne / xg))
+            e = f32(0); ne_prev = ne; D_prev = f32(0)

@@ -41,5 +41,8 @@ def test_certified_decisions_equal_reference(S, B, T, W, D, c_puct):
     assert stats.bad_stop == 0 and stats.bad_action == 0, 'a certified decision differs from the reference'
     # the bound holds with room on every evaluation that went through (quantities are <= 1 ulp apart when the ratio nears 1)
     assert stats.max_ne_ratio <= 1. and stats.max_cum_ratio <= 1. and stats.max_alpha_ratio <= 1.
+    # the kernel's complete control flow (fast iterations from a safe point, single exact passes on demand) resolves every
+    # flagged evaluation to the reference's action and pass count
+    assert stats.resolved > 0 and stats.bad_resolved == 0
     flagged = stats.flag_stop + stats.flag_sample + stats.flag_guard + stats.flag_tiny
     assert flagged / stats.evals < .05

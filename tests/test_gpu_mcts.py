@@ -150,7 +150,7 @@ def _engine_stepwise_vs_oracle(S, B, T, W, D, extreme):
     A = S * S
 
     o = pyref.Tree(w0, n_nodes=T)
-    eng = SearchEngine(B, S, T, 'cuda', mirror_logits=True)
+    eng = SearchEngine(B, S, T, 'cuda', mirror_logits=True, fast_descent=True)
     eng.reset(w0.board.cuda(), w0.seats.cuda(), 1 / 16)
     o.initialize(onet)
     # the engine receives the oracle's (noised) root evaluation verbatim
