@@ -28,13 +28,25 @@ SOURCES = {
     'descend.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'] + (['-DBL_CHILD_ILP=' + os.environ['BL_CHILD_ILP']] if 'BL_CHILD_ILP' in os.environ else []),
     'descend_mw.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
     'descend_fx.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
-    'descend_pc.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
+    'experimental.cu': [],
     'net.cu': [],
     'net_tc.cu': [],
     'net_tc_wide.cu': [],
     'learner.cu': [],
     'host.cu': [],
 }
+
+
+# Measured-and-rejected descent variants (4 = producer/consumer warps, 6 = speculative evaluation of every node):
+# bit-exact but slower than the default, so they stay out of the product library unless BL_EXPERIMENTAL=1 is set at build time
+# (tests/test_gpu_mcts.py and tests/test_gpu_fx.py skip them when they are not compiled in).
+EXPERIMENTAL = {
+    'descend_all.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
+    'descend_pc.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
+}
+if os.environ.get('BL_EXPERIMENTAL') == '1':
+    del SOURCES['experimental.cu']
+    SOURCES.update(EXPERIMENTAL)
 
 
 def nvcc():
@@ -55,6 +67,10 @@ def build(force=False, verbose=False):
     OBJ.mkdir(exist_ok=True)
     headers = list(CSRC.glob('*.cuh')) + [HERE.parent / 'include' / 'boardlaw_b200.h', Path(__file__)]
     objs, procs = [], []
+    for stale in list(EXPERIMENTAL) + ['experimental.cu']:                 # objects of the other configuration must not be linked
+        if stale not in SOURCES and (OBJ / (Path(stale).stem + '.o')).exists():
+            (OBJ / (Path(stale).stem + '.o')).unlink()
+            force = True
     for name, extra in SOURCES.items():
         src = CSRC / name
         if not src.exists():

@@ -514,9 +514,10 @@ int child_cap(const bl_tree *t) { return t->A < t->T - 1 ? t->A : (t->T > 1 ? t-
 extern "C" int64_t bl_tree_scratch_bytes(const bl_tree *t) {
     const int64_t lanes_needed = ((int64_t)t->B + 31) / 32 * 32, lanes_max = (int64_t)BL_NUM_SMS * 32 * 32;
     const int64_t v3 = (lanes_needed < lanes_max ? lanes_needed : lanes_max) * child_cap(t) * (int64_t)sizeof(ChildEntry);
-    const int64_t mw = bl_mw_scratch_bytes(t), fx = bl_fx_scratch_bytes(t);
-    const int64_t m = v3 > mw ? v3 : mw;
-    return m > fx ? m : fx;
+    const int64_t mw = bl_mw_scratch_bytes(t), fx = t->cpi ? bl_fx_scratch_bytes(t) : 0, al = t->cpi ? bl_all_scratch_bytes(t) : 0;
+    int64_t m = v3 > mw ? v3 : mw;
+    m = m > fx ? m : fx;
+    return m > al ? m : al;
 }
 
 int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st) {

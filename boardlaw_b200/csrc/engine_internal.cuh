@@ -70,6 +70,11 @@ int64_t bl_mw_scratch_bytes(const bl_tree *t);
 // bound, exact path otherwise; followed by expand + env step.  -2 = unsupported shape
 int bl_descend_fx(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
 int64_t bl_fx_scratch_bytes(const bl_tree *t);
+// descend_all.cu: speculative descent (variant 6): every node evaluated independently (certified closed form), then a pointer chase
+// + expand + env step.  -2 = unsupported shape, -3 = scratch too small
+int bl_descend_all(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
+int64_t bl_all_scratch_bytes(const bl_tree *t);
+bool bl_experimental_built();      // variants 4 and 6 are compiled in (BL_EXPERIMENTAL=1 at build time)
 // descend.cu: expand + env step of the descents recorded in t.leaf / leaf_parent / leaf_action
 int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st);
 // descend.cu: device buffer of the optional phase clock (NULL = off); slots 0..15 descent, 16..31 network

@@ -47,7 +47,7 @@ class SearchEngine:
             prior=z((B, A), torch.float16), qrange=z((T + 1, 2), torch.float32), counters=z((16,), torch.int64))
         # the certified fast descent (variant 5) samples from the prefix sums of the pi rows: three more arrays
         if fast_descent is None:
-            fast_descent = os.environ.get('BL_DESCEND_VARIANT') == '5'
+            fast_descent = os.environ.get('BL_DESCEND_VARIANT') in ('5', '6')
         if fast_descent:
             self.ws.update(cpi=z((B, T, self.AP), torch.float32), psum=z((B, T), torch.float32), cprior=z((B, T), torch.float32))
         if mirror_logits:

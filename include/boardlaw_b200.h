@@ -246,9 +246,12 @@ int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint
  *     when the bound does not separate it (bit-identical results, fewer instructions, but not faster: DESIGN.md 5.1c),
  * 2 = task-parallel descent, one lane per env with register-resident rows (descend.cu),
  * 3 = two or four lanes per env: terms split over the lanes, the S and g chains on two of them (descend_mw.cu),
+ * 6 = speculative descent (descend_all.cu; same requirements as 5): the certified evaluation of EVERY node of every tree, independently
+ *     (a node's sampled action does not depend on how it was reached), then a pointer chase from the root,
  * 4 = experimental: passes and node services on different warps of a CTA (descend_pc.cu; measured slower),
  * 1 = one lane per env in lock step, reference loops verbatim (engine.cu; kept as an on-device cross-check).
- * All produce identical results (tests/test_gpu_mcts.py runs the oracle comparison for each). */
+ * All produce identical results (tests/test_gpu_mcts.py runs the oracle comparison for each).  4 and 6 were measured slower and are
+ * compiled in only when the library is built with BL_EXPERIMENTAL=1; without it the call returns -2 for them. */
 int bl_debug_set_descend_variant(int variant);
 
 /* Caps the number of warps of the one-lane descent (variant 2): with fewer lanes than envs the lanes pull envs from a global

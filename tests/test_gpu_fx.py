@@ -37,7 +37,8 @@ def _search(eng, worlds, net, variant, draw, grid=0):
     """One whole eager search with the in-kernel random stream of move 0; returns clones of the tree and the outputs."""
     from boardlaw_b200 import _lib
     lib = _lib.lib()
-    lib.bl_debug_set_descend_variant(variant)
+    if lib.bl_debug_set_descend_variant(variant) != 0:
+        return None                                                # not compiled in (BL_EXPERIMENTAL=1 at build time)
     lib.bl_debug_set_descend_grid(grid)
     try:
         eng.move = 0
@@ -55,6 +56,8 @@ def _search(eng, worlds, net, variant, draw, grid=0):
 
 
 def _assert_same(a, b, what):
+    if b is None:
+        return
     for k in TREE_FIELDS:
         assert torch.equal(a[k], b[k]), f'{what}: {k} differs'
     assert a['pi'] == b['pi'], f'{what}: pi rows differ'
@@ -78,6 +81,7 @@ def test_descent_variants_full_batch(S, B, T, W, D):
     ref = _search(eng, worlds, net, 2, draw)
     fx = _search(eng, worlds, net, 5, draw)
     _assert_same(ref, fx, 'variant 5 vs 2')
+    _assert_same(ref, _search(eng, worlds, net, 6, draw), 'variant 6 vs 2')
     evals = fx['counters'][0]
     flagged = sum(fx['counters'][8:11])
     print(f'\nS{S} B{B}: {evals} evaluations, {flagged} sent to the exact path ({100 * flagged / max(evals, 1):.3f} %: stop '
@@ -213,12 +217,13 @@ def test_tree_mode_equals_plain_mode_w256():
     assert torch.equal(eng.ws.pi[envs, leaf][:, :S * S], want_pi)
 
 
-@pytest.mark.parametrize('variant', [5, 3, 2])
+@pytest.mark.parametrize('variant', [6, 5, 3, 2])
 def test_engine_stepwise_vs_oracle_t256(variant):
     """c3's tree depth: S11, T = 256 (four 64-bit words of children mask per node) stepwise against the oracle."""
     import test_gpu_mcts as tm
     from boardlaw_b200 import _lib
-    _lib.lib().bl_debug_set_descend_variant(variant)
+    if _lib.lib().bl_debug_set_descend_variant(variant) != 0:
+        pytest.skip(f'descent variant {variant} is not compiled in')
     try:
         tm._engine_stepwise_vs_oracle(11, 40, 256, 32, 2, False)
     finally:
