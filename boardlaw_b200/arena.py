@@ -66,6 +66,7 @@ def evaluate(worlds, agents):
     moves = torch.zeros((B,), dtype=torch.int, device=dev)
     times = torch.zeros((B,), dtype=torch.float, device=dev)
     matchup_idxs = matchup_indices(B, worlds.n_seats).to(dev)
+    errors = torch.zeros((), dtype=torch.int32, device=dev)      # rule violations of every step of the evaluation (Hex.step)
     while True:
         for i, (_, agent) in enumerate(agents):
             idx = ((matchup_idxs[envs, worlds.seats.long()] == i) & ~terminal).nonzero().squeeze(-1)
@@ -73,10 +74,13 @@ def evaluate(worlds, agents):
                 continue
             start = time.time()
             sub = worlds[idx]
+            sub.errors = errors
             decisions = agent(sub, eval=True)
             stepped, transitions = sub.step(decisions.actions)
             worlds[idx] = stepped
             terminal[idx] = transitions.terminal
+            if dev.type == 'cuda':
+                torch.cuda.synchronize(dev)                          # the clock below measures the move, not its launch
             end = time.time()
 
             wins[idx] += (transitions.rewards == 1).int()
@@ -84,4 +88,6 @@ def evaluate(worlds, agents):
             times[idx] += (end - start) / idx.numel()
         if bool(terminal.all()):
             break
+    if int(errors) != 0:
+        raise AssertionError(f'an agent played an invalid action during the evaluation (error bits {int(errors):#x})')
     return gather(wins.cpu(), moves.cpu(), times.cpu(), matchup_idxs.cpu(), agents, worlds.boardsize)

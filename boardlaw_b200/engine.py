@@ -80,10 +80,29 @@ class SearchEngine:
         self._scratch = None
         self._scratch_key = None
         self._graphs = {}
+        self._graph_refs = {}      # key -> the staged operand tensors the graphs of that key point into
+        self._graph_lru = []       # least recently used first; at most MAX_GRAPH_KEYS (network, c_puct) combinations stay captured
         self.sim = 0
         self.move = 0
         self.launches = 0          # kernels of libboardlaw_b200.so launched (or replayed from a graph) so far
         self._graph_launches = {}
+
+    MAX_GRAPH_KEYS = 4
+
+    def _touch(self, key):
+        if key in self._graph_lru:
+            self._graph_lru.remove(key)
+        self._graph_lru.append(key)
+        while len(self._graph_lru) > self.MAX_GRAPH_KEYS:
+            old = self._graph_lru.pop(0)
+            for part in ('head', 'sims'):
+                self._graphs.pop((part,) + old, None)
+                self._graph_launches.pop((part,) + old, None)
+            self._graph_refs.pop(old, None)
+
+    def release(self):
+        """Drops the captured graphs (they pin the workspace and the networks' staged operands)."""
+        self._graphs.clear(); self._graph_launches.clear(); self._graph_refs.clear(); self._graph_lru.clear()
 
     # ---- thin wrappers over the C ABI ------------------------------------------------------------------
     def _stream(self):
@@ -204,7 +223,11 @@ class SearchEngine:
         self.in_seats.copy_(seats)
         self.ws.counters[6:7].fill_(self.move)       # keys the in-kernel random stream of this move
         self.move += 1
-        key = (cparams.W, cparams.D, cparams.precision, float(c_puct), id(network), network._pack_gen)
+        # graphs bake in the addresses of the network's staged operands: key on the model's own token (CPython reuses id() values once a
+        # model is collected) and on the staging generation, and keep the operands alive for as long as the graph is cached
+        key = (cparams.W, cparams.D, cparams.precision, float(c_puct), network.token, network._pack_gen)
+        self._graph_refs[key] = network._pack
+        self._touch(key)
         if not use_graph:
             self._reset(c_puct)
             self.eval_root(cparams)

@@ -69,13 +69,30 @@ class Hex(arrdict.namedarrtuple('Hex', fields=('board', 'seats'))):
             assert (0 <= actions).all(), 'You passed a negative action'
             assert self.valid.gather(1, actions[:, None]).squeeze(-1).all()
 
-        errors = self.board.new_zeros((), dtype=torch.int32)
+        errors = self._error_word()
         new_board, new_seats, rewards, terminal = cuda.transition(
             self.board.contiguous(), self.seats.int().contiguous(), actions, reset, errors)
         new_world = type(self)(board=new_board, seats=new_seats)
         new_world.errors = errors
         transition = arrdict.arrdict(terminal=terminal, rewards=rewards)
         return new_world, transition
+
+    def _error_word(self):
+        """One int32 on the device per chain of worlds: ``step`` ORs rule violations into it (bit 0: negative / out-of-range
+        action, bit 1: occupied cell) and hands the same tensor to the world it returns, so a whole loop of steps costs one
+        allocation and can be checked once, at a point where the host synchronises anyway (``check()``)."""
+        errors = getattr(self, 'errors', None)
+        if errors is None or errors.device != self.board.device:
+            errors = self.board.new_zeros((), dtype=torch.int32)
+        return errors
+
+    def check(self):
+        """Raises if any step of the chain that led to this world broke the rules (the reference asserts on the host inside every
+        step, boardlaw/hex/__init__.py:174-179: two device syncs per step; ``STRICT = True`` restores that).  Synchronises."""
+        errors = getattr(self, 'errors', None)
+        if errors is not None and int(errors) != 0:
+            raise AssertionError(f'invalid action(s) were played (error bits {int(errors):#x}: 1 = negative or out of range, 2 = occupied cell)')
+        return self
 
 
     def step_random(self, uniforms=None, generator=None, reset=True):
@@ -85,7 +102,7 @@ class Hex(arrdict.namedarrtuple('Hex', fields=('board', 'seats'))):
         (new_world, arrdict(terminal, rewards, actions))."""
         if uniforms is None:
             uniforms = torch.rand((self.n_envs,), device=self.device, generator=generator)
-        errors = self.board.new_zeros((), dtype=torch.int32)
+        errors = self._error_word()
         new_board, new_seats, actions, rewards, terminal = cuda.random_transition(
             self.board.contiguous(), self.seats.int().contiguous(), uniforms.float().contiguous(), reset, errors)
         new_world = type(self)(board=new_board, seats=new_seats)

@@ -14,17 +14,28 @@ from .mcts import MCTSAgent
 from .networks import FCModel
 
 
+def setup(boardsize, width, depth, nodes=64, c_puct=1 / 16, n_envs=32 * 1024, mix_steps=None, device='cuda', seed=0, rank=0):
+    """(worlds, network, agent) of one rank.  What must be IDENTICAL on every rank is drawn from ``seed``: the network's initial
+    weights (and, in ``run``, the chunk sampler's indices); what must DIFFER is drawn from ``seed + 1 + rank``: the decorrelating
+    playouts, the Dirichlet noise, the sampled actions and the engine's in-kernel random stream — otherwise every rank would play
+    the same games and the gathered chunk would hold world_size copies of one shard."""
+    torch.manual_seed(seed)
+    probe = Hex.initial(1, boardsize, device=device)
+    network = FCModel(probe.obs_space, probe.action_space, width=width, depth=depth).to(probe.device)
+    torch.manual_seed(seed + 1 + rank)
+    worlds = learning.mix(Hex.initial(n_envs, boardsize, device=device), T=2500 if mix_steps is None else mix_steps)   # main.py:150
+    agent = MCTSAgent(network, n_nodes=nodes, c_puct=c_puct, engine_seed=seed + 1 + rank)
+    return worlds, network, agent
+
+
 def run(boardsize, width, depth, nodes=64, c_puct=1 / 16, lr=1e-3, n_envs=32 * 1024, buffer_len=64, mix_steps=None, max_steps=1,
         device='cuda', pool=None, seed=0, on_step=None):
     """Returns (agent, list of arrdict(policy_loss, value_loss) per optimiser step).  ``n_envs`` is per rank; ``pool`` a
     ``selfplay.TrajectoryPool`` when running under torch.distributed (None: single process)."""
-    torch.manual_seed(seed)
-    worlds = learning.mix(Hex.initial(n_envs, boardsize, device=device), T=2500 if mix_steps is None else mix_steps)   # main.py:150
-    network = FCModel(worlds.obs_space, worlds.action_space, width=width, depth=depth).to(worlds.device)
-    agent = MCTSAgent(network, n_nodes=nodes, c_puct=c_puct)
-    L = learner.Learner(network, lr=lr)
     pool = pool or selfplay.TrajectoryPool()
-    world_size = pool.world
+    world_size, rank = pool.world, pool.rank
+    worlds, network, agent = setup(boardsize, width, depth, nodes, c_puct, n_envs, mix_steps, device, seed, rank)
+    L = learner.Learner(network, lr=lr)
     g = torch.Generator(device=worlds.device).manual_seed(seed)                   # same draw on every rank
     n_all = n_envs * world_size
     idxs = (torch.randint(buffer_len, (n_all,), device=worlds.device, generator=g), torch.arange(n_all, device=worlds.device))   # main.py:170
@@ -36,8 +47,10 @@ def run(boardsize, width, depth, nodes=64, c_puct=1 / 16, lr=1e-3, n_envs=32 * 1
             pool.gather(selfplay.pack_records(worlds, decisions, transition))
             records.append(pool.wait().clone())
             worlds = new_worlds
+        worlds.check()                                                              # rule violations recorded on the device by Hex.step
         chunk, records = learner.chunk_from_records(records, boardsize, n_all)    # main.py:188
         out = L.optimize(chunk[idxs])                                              # main.py:189
+        selfplay.check_replicas(network, pool)                                      # every rank applied the same update to the same weights
         losses.append(out)
         if on_step is not None:
             on_step(step, agent, out)

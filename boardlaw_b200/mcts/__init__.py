@@ -169,35 +169,38 @@ class EngineSearch:
 _engines = {}
 
 
-def engine_for(world, n_nodes):
+def engine_for(world, n_nodes, seed=0):
     """Workspaces are persistent: one per (device, capacity, boardsize, n_nodes), reused move after move.  A batch smaller than
     an existing workspace of the same shape runs inside it (``SearchEngine._search_partial``): arena-style callers, whose
     sub-batch shrinks every move as games end, allocate once."""
     from ..engine import SearchEngine
-    key = (str(world.device), world.n_envs, world.boardsize, n_nodes)
+    key = (str(world.device), world.n_envs, world.boardsize, n_nodes, seed)
     if key in _engines:
         return _engines[key]
     fits = [k for k in _engines if k[0] == key[0] and k[2:] == key[2:] and world.n_envs < k[1] <= 4 * max(world.n_envs, 256)]
     if fits:
         return _engines[min(fits, key=lambda k: k[1])]
     if len(_engines) >= 4:
-        _engines.pop(next(iter(_engines)))
-    _engines[key] = SearchEngine(world.n_envs, world.boardsize, n_nodes, world.device)
+        _engines.pop(next(iter(_engines))).release()      # its CUDA graphs would keep the whole workspace alive
+    _engines[key] = SearchEngine(world.n_envs, world.boardsize, n_nodes, world.device, seed=seed)
     return _engines[key]
 
 
 def _fusable(worlds, network):
     from ..hex import Hex
     from ..networks import FCModel
-    return isinstance(worlds, Hex) and isinstance(network, FCModel) and worlds.board.ndim == 3 and worlds.device.type == 'cuda'
+    # the engine's node records hold actions in a byte and node ids in 16 bits (check_tree, csrc/engine.cu)
+    return (isinstance(worlds, Hex) and isinstance(network, FCModel) and worlds.board.ndim == 3 and worlds.device.type == 'cuda'
+            and worlds.boardsize ** 2 <= 255)
 
 
-def mcts(worlds, network, n_nodes=64, c_puct=1 / 16, noise_eps=.25, alpha_scale=10, fused=None, **kwargs):
+def mcts(worlds, network, n_nodes=64, c_puct=1 / 16, noise_eps=.25, alpha_scale=10, fused=None, engine_seed=0, **kwargs):
     """boardlaw/mcts/__init__.py:200-207.  Hex worlds with an FCModel run on the fused engine; anything else (toy
-    worlds, arbitrary network callables) runs the op-level ``MCTS`` loop."""
+    worlds, arbitrary network callables, boards of 16x16 and more) runs the op-level ``MCTS`` loop.  ``engine_seed`` keys the
+    engine's in-kernel random stream (one per rank in multi-process runs)."""
     fused = _fusable(worlds, network) if fused is None else fused
-    if fused and n_nodes > 1:
-        eng = engine_for(worlds, n_nodes)
+    if fused and 1 < n_nodes <= 32767:
+        eng = engine_for(worlds, n_nodes, engine_seed)
         out = eng.search(worlds.board, worlds.seats, network, c_puct=c_puct, noise_eps=noise_eps, alpha_scale=alpha_scale, **kwargs)
         return EngineSearch(eng, out)
     m = MCTS(worlds, n_nodes=n_nodes, c_puct=c_puct, noise_eps=noise_eps, alpha_scale=alpha_scale)

@@ -73,11 +73,22 @@ def mcts(logits, w, n, c_puct, seats, terminal, children):
     return MCTS(logits, w, n, c_puct, seats.short() if seats.dtype != torch.int16 else seats, terminal, children)
 
 
+_next_rands = []
+
+
+def inject_rands(rands):
+    """The next ``descend`` call without a ``rands`` argument uses this (B,T) half tensor instead of drawing one: lets a caller
+    that cannot pass the argument (the reference's ``MCTS.descend`` calls ``descend(m)``) run a seeded comparison across devices."""
+    _next_rands.append(rands)
+
+
 def descend(m, rands=None):
     """``mctscuda.descend`` (boardlaw/mcts/cpp/cuda.cu:184-203).  ``rands`` (B,T) half is drawn here with
     ``torch.rand_like`` exactly where the reference draws it, unless injected."""
     B, T, A = m.logits.shape
     Sn = m.w.shape[2]
+    if rands is None and _next_rands:
+        rands = _next_rands.pop(0)
     if rands is None:
         rands = torch.rand_like(m.logits[:, :, 0])
     rands = proxy(rands.contiguous(), torch.float16, 2, 'rands')

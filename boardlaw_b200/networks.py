@@ -59,6 +59,7 @@ class FCModel(nn.Module):
         self._pack_gen = 0          # bumped whenever the staged operands move to new device addresses (captured graphs key on it)
         # False routes every shape through the CUDA-core fp32 kernels (net.cu) — used as the on-device cross-check
         self.tensor_cores = True
+        self.token = next(_TOKENS)
         # tile order of the packed operands (bl_fc_params.tc_nsplit); BL_TC_NSPLIT overrides for experiments
         import os
         self.tc_nsplit = 1      # whole-N tiles: one tcgen05.mma issue costs ~120 cycles, so N = W/2 tiles are issue-bound
@@ -131,6 +132,9 @@ class FCModel(nn.Module):
             logits, v = self.evaluate(worlds.board, worlds.seats)
         return arrdict.arrdict(logits=logits, v=v)
 
+
+import itertools
+_TOKENS = itertools.count(1)     # identity of an FCModel for caches that outlive it (id() values are reused by CPython)
 
 KC = 32     # K elements per operand tile (net_tc.cu)
 

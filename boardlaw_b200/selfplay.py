@@ -85,6 +85,7 @@ class TrajectoryPool:
             with torch.cuda.stream(self._side):
                 dist.all_gather_into_tensor(out, rec, group=self.group)
                 rec.record_stream(self._side)
+                out.record_stream(self._side)     # allocated on the caller's stream, written on this one
             self._pending = (out, self._side)
         else:
             try:
@@ -118,6 +119,26 @@ class SelfPlay:
             self.pool.gather(pack_records(self.worlds, decisions, transitions))
         self.worlds = new_worlds
         return decisions, transitions
+
+
+def weight_checksum(network):
+    """A float64 fingerprint of every parameter (sum and sum of squares), cheap enough to compare after every optimiser step."""
+    ps = [p.detach().double().reshape(-1) for p in network.parameters()]
+    flat = torch.cat(ps) if ps else torch.zeros(0, dtype=torch.double)
+    return torch.stack([flat.sum(), (flat * flat).sum()])
+
+
+def check_replicas(network, pool):
+    """Raises if the ranks' replicas of ``network`` have drifted apart: the env-sharded loop relies on every rank applying the same
+    deterministic update to identical weights (no weight broadcast).  One 16-byte all-gather."""
+    if pool is None or pool.world == 1:
+        return
+    mine = weight_checksum(network)
+    out = [torch.empty_like(mine) for _ in range(pool.world)]
+    dist.all_gather(out, mine, group=pool.group)
+    for r, other in enumerate(out):
+        if not torch.equal(other, out[0]):
+            raise RuntimeError(f'rank {r} holds different network weights than rank 0 (checksums {other.tolist()} vs {out[0].tolist()})')
 
 
 def shard_bounds(n_envs, world, rank):

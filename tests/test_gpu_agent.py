@@ -139,3 +139,67 @@ def test_fused_agent_vs_oracle_agreement():
     frac_tree, frac_policy = same_tree.float().mean().item(), same_policy.float().mean().item()
     print(f'identical trees: {frac_tree:.4f}, identical root policies: {frac_policy:.4f}')
     assert frac_tree >= 0.9
+
+
+def test_rank_seeds_split():
+    """main.setup: ranks share the network's initial weights and differ in everything that is drawn during play."""
+    from boardlaw_b200 import main
+    w0, n0, a0 = main.setup(5, 32, 2, nodes=8, n_envs=64, mix_steps=12, seed=3, rank=0)
+    w1, n1, a1 = main.setup(5, 32, 2, nodes=8, n_envs=64, mix_steps=12, seed=3, rank=1)
+    for (k, p), (_, q) in zip(n0.state_dict().items(), n1.state_dict().items()):
+        assert torch.equal(p, q), f'{k} differs between ranks'
+    assert not torch.equal(w0.board, w1.board), 'both ranks decorrelated their worlds with the same playouts'
+    # same position, same torch seed: the engines' in-kernel random streams still differ by rank
+    torch.manual_seed(0); d0 = a0(w0)
+    torch.manual_seed(0); d1 = a1(w0)
+    assert not torch.equal(d0.logits, d1.logits)
+
+
+def test_hex_error_word_persists_and_check_raises():
+    from boardlaw_b200.hex import Hex
+    w = Hex.initial(8, 5, device='cuda')
+    a = torch.zeros(8, dtype=torch.long, device='cuda')
+    w1, _ = w.step(a)
+    w1.check()
+    w2, _ = w1.step((a + 1))
+    assert w2.errors.data_ptr() == w1.errors.data_ptr(), 'one error word per chain of worlds'
+    w3, _ = w2.step(a)                                    # cell 0 is occupied (black's first move; white's frame is transposed: (0,0) again)
+    w4, _ = w3.step(a + 7)                                # a legal move afterwards does not clear the record
+    with pytest.raises(AssertionError):
+        w4.check()
+
+
+def test_graph_cache_survives_model_replacement():
+    """Graphs are keyed on a per-model token, not id(): a new model of the same shape (possibly at the same address) gets its own."""
+    import gc
+    from boardlaw_b200.hex import Hex
+    from boardlaw_b200.mcts import engine_for
+    worlds = Hex.initial(64, 5, device='cuda')
+    outs = []
+    for seed in (1, 2, 3, 4, 5, 6):
+        agent, _ = make_agent(5, 32, 2, 8, seed=seed)
+        torch.manual_seed(0)
+        d = agent(worlds, eval=True)
+        ref = agent.network(worlds)
+        # node 0's prior is the network's own policy mixed with noise: check against an un-graphed search of the same model
+        torch.manual_seed(0)
+        d2 = agent(worlds, eval=True, use_graph=False)
+        assert torch.equal(d.logits, d2.logits) and torch.equal(d.v, d2.v)
+        outs.append(d.v.clone())
+        del agent
+        gc.collect()
+    eng = engine_for(worlds, 8)
+    assert len(eng._graph_lru) <= eng.MAX_GRAPH_KEYS and len(eng._graphs) <= 2 * eng.MAX_GRAPH_KEYS
+    assert not all(torch.equal(outs[0], o) for o in outs[1:])
+
+
+def test_large_board_falls_back_to_op_level():
+    """16x16 has 256 actions, one more than the engine's node records hold: mcts() must take the op-level path, not fail."""
+    from boardlaw_b200.hex import Hex
+    from boardlaw_b200.mcts import MCTS, mcts
+    agent, _ = make_agent(16, 32, 1, 4)
+    worlds = Hex.initial(6, 16, device='cuda')
+    m = mcts(worlds, agent.network, n_nodes=4)
+    assert isinstance(m, MCTS)
+    d = agent(worlds)
+    assert worlds.valid.gather(1, d.actions[:, None]).all()

@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from boardlaw_b200 import arrdict
-from boardlaw_b200.selfplay import TrajectoryPool, pack_records, record_width, shard_bounds, unpack_records
+from boardlaw_b200.selfplay import TrajectoryPool, check_replicas, pack_records, record_width, shard_bounds, unpack_records, weight_checksum
 
 
 def _free_port():
@@ -70,6 +70,17 @@ def _worker(rank, world, port, S, B, out):
             assert got.shape == (world, B, record_width(S * S))
             for r in range(world):                      # every rank sees every shard's records, in rank order
                 _check_roundtrip(got[r], S, *_fake_move(B, S, seed=100 * move + r))
+        # replica check of the env-sharded actor/learner loop (main.run): identical weights pass, a drifted replica raises everywhere
+        torch.manual_seed(0)
+        net = torch.nn.Linear(7, 5)
+        check_replicas(net, pool)
+        with torch.no_grad():
+            net.weight[0, 0] += float(rank)
+        try:
+            check_replicas(net, pool)
+            raise AssertionError('drifted replicas were not detected')
+        except RuntimeError as e:
+            assert 'different network weights' in str(e)
         out.put((rank, 'ok'))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))
@@ -88,3 +99,13 @@ def test_trajectory_allgather_world2():
     for p in procs:
         p.join(timeout=60)
     assert results == {0: 'ok', 1: 'ok'}, results
+
+
+def test_weight_checksum_detects_a_changed_parameter():
+    torch.manual_seed(1)
+    a, b = torch.nn.Linear(9, 4), torch.nn.Linear(9, 4)
+    b.load_state_dict(a.state_dict())
+    assert torch.equal(weight_checksum(a), weight_checksum(b))
+    with torch.no_grad():
+        b.bias[2] += 1e-6
+    assert not torch.equal(weight_checksum(a), weight_checksum(b))
