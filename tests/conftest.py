@@ -16,3 +16,14 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden_dir():
     return ROOT / 'tests' / 'golden'
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests need a CUDA device: without one they are skipped rather than failed (the driver selects with -m anyway)."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason='no CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
