@@ -28,7 +28,7 @@ CONFIGS = {
     'c5-5': (5, 32768, 64, 256, 4), 'c5-7': (7, 32768, 64, 256, 4), 'c5-9': (9, 32768, 64, 256, 4),
     'c5-11': (11, 32768, 64, 256, 4), 'c5-13': (13, 32768, 64, 256, 4),
 }
-CPU_SAMPLE_ENVS = {'c1': 256, 'c2': 1024, 'c3': 64}      # ~10-20 s of host work per leg (cost is linear in envs: serial per-env loops)
+CPU_SAMPLE_ENVS = {'c1': 256, 'c2': 2048, 'c3': 64}      # 2 048 envs at c2 (cost is linear in envs: serial per-env loops), ~8 s per move
 
 
 def describe(config):
@@ -112,18 +112,28 @@ def algorithmic_bytes(S, T, counters, n_desc):
     return {'descend_expand': descend + expand_step, 'net': net_io, 'backup': backup}
 
 
-def ncu_traffic(kind):
-    """dram read + write bytes per launch of the dominant kernel, from the committed ``ncu --set full`` summary (profiles/)."""
-    name = {'descend_expand': 'r01_descend_v3c_ncu_full.txt', 'net': 'r01_fc_tc_v2_ncu_full.txt', 'backup': 'r01_backup_v2_ncu_full.txt'}.get(kind)
-    f = ROOT / 'profiles' / name if name else None
-    if not f or not f.exists():
-        return None
-    total, scale = 0., {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-    for line in f.read_text().splitlines():
-        if line.startswith('dram__bytes_read.sum [') or line.startswith('dram__bytes_write.sum ['):
-            unit = line.split('[')[1].split(']')[0]
-            total += float(line.split('=')[1]) * scale.get(unit, 1)
-    return total or None
+def source_sha():
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted((ROOT / 'boardlaw_b200' / 'csrc').glob('*.cu*')):
+        h.update(f.name.encode()); h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kind, config):
+    """dram read + write bytes per launch of a kernel class, mean over every launch of one move, from the capture taken by
+    tools/capture_traffic.py (profiles/r02_traffic_<config>.json).  None when there is no capture for this config or the kernel
+    sources have changed since it was taken (the file records their sha1)."""
+    f = ROOT / 'profiles' / f'r02_traffic_{config.split("-")[0] if config.startswith("c5-9") else config}.json'
+    if not f.exists():
+        return None, 'no capture for this config'
+    d = json.loads(f.read_text())
+    if d.get('source_sha') != source_sha():
+        return None, f'capture {f.name} is of other kernel sources (sha {d.get("source_sha")})'
+    c = d['classes'].get(kind)
+    if not c:
+        return None, 'kernel class not in the capture'
+    return c['dram_bytes_per_launch'], f'{f.name}: {c["kernel"]}, {c["launches"]} launches, {c["registers"]} registers'
 
 
 def net_flops(S, W, D):
@@ -163,6 +173,84 @@ def kernel_split(agent, worlds, T, n_moves=2):
             acc[kind] += a.elapsed_time(b)
     counters = eng.ws.counters.cpu().tolist()
     return {k: v / n_moves for k, v in acc.items()}, [c / n_moves for c in counters], {k: v // n_moves for k, v in launches.items()}
+
+
+def time_hex_step(worlds, hbm_peak, hbm_src, reps=20):
+    """The env transition of the real worlds (bl_hex_transition: copy + move + auto-reset, one launch per move) on its own:
+    algorithmic bytes 2A + 8 + 2*Sn*4 + 1 per env (board in and out, seats, rewards, terminal)."""
+    import torch
+    A = worlds.boardsize ** 2
+    actions = torch.multinomial(worlds.valid.float(), 1).squeeze(-1)
+    worlds.step(actions)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        worlds.step(actions)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    nbytes = worlds.n_envs * (2 * A + 8 + 16 + 1 + 8)
+    gbs = nbytes / (us * 1e-6) / 1e9
+    return {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'peak_source': hbm_src,
+            'us_per_launch': us, 'algorithmic_bytes_per_launch': nbytes, 'traffic': None,
+            'note': 'includes the torch allocations of Hex.step\'s outputs; at 5.7 MB per launch the kernel is launch/latency-bound, not HBM-bound'}
+
+
+def run_leg(leg, config, timeout=900):
+    """Runs one baseline leg (``--leg``) of this script in a fresh process and returns the JSON object it prints."""
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / 'bench.py'), '--leg', leg, '--config', config], capture_output=True, text=True, timeout=timeout)
+        for line in reversed(r.stdout.splitlines()):
+            if line.startswith('{'):
+                return json.loads(line)
+        return {'unavailable': (r.stderr or r.stdout)[-300:]}
+    except Exception as e:                      # informational legs never take the bench line down
+        return {'unavailable': f'{type(e).__name__}: {e}'[:300]}
+
+
+def measure_config(config, precision='fp32', steps=2, warmup=3):
+    """value (sims/s) and ms per move of one more config, through SelfPlay.step as the headline (device-resident worlds)."""
+    import torch
+    from boardlaw_b200 import heads, mcts
+    from boardlaw_b200.mcts import MCTSAgent
+    from boardlaw_b200.networks import FCModel, synthetic_state_dict
+    from boardlaw_b200.selfplay import SelfPlay
+    S, B, T, W, D = CONFIGS[config]
+    device = torch.device('cuda', torch.cuda.current_device())
+    net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(S * S), width=W, depth=D, precision=precision)
+    net.load_state_dict(synthetic_state_dict(S, W, D, seed=0))
+    agent = MCTSAgent(net.to(device), n_nodes=T, c_puct=1 / 16)
+    torch.manual_seed(0)
+    play = SelfPlay(make_worlds(S, B, device, seed=0), agent, None)
+    for _ in range(warmup):
+        play.step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        play.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del play, agent, net
+    for eng in list(mcts._engines.values()):
+        eng.release()
+    mcts._engines.clear()
+    torch.cuda.empty_cache()
+    return {'value': B * T / (ms / 1e3), 'unit': 'sims/s', 'ms_per_step': ms, 'steps': steps, 'workload': describe(config), 'net_precision': precision}
+
+
+def run_extras(args):
+    """The other BASELINE.json configs on this GPU, a few moves each (device-timed as `value`): c3, the c5 board-size sweep, and c2 with the
+    reference's own GPU precision class (fp16 autocast, boardlaw/mcts/__init__.py:131-133)."""
+    out = {}
+    for name, precision in [('c2', 'amp'), ('c5-5', 'fp32'), ('c5-7', 'fp32'), ('c5-11', 'fp32'), ('c5-13', 'fp32'), ('c3', 'fp32')]:
+        try:
+            out[name + ('-amp' if precision == 'amp' else '')] = measure_config(name, precision)
+        except Exception as e:
+            out[name] = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
+    return out
 
 
 def run_ours(args):
@@ -285,28 +373,44 @@ def run_ours(args):
         n_desc = B * (T - 1)
         bytes_by = algorithmic_bytes(S, T, counters, n_desc)
         dominant = max(('descend_expand', 'net', 'backup'), key=lambda k: split[k])
-        if dominant == 'net':
-            flops = net_flops(S, W, D) * n_desc
-            achieved = flops / (split['net'] / 1e3) / 1e12
-            roofline = {'kernel': 'fc_forward (leaf evaluation)', 'bound': 'tensor', 'achieved': achieved, 'peak': tc_peak,
-                        'unit': 'TFLOP/s', 'frac': achieved / tc_peak, 'traffic': ncu_traffic('net'),
-                        'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback'}
-        else:
-            achieved = bytes_by[dominant] / (split[dominant] / 1e3) / 1e9
-            roofline = {'kernel': dominant, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                        'frac': achieved / hbm_peak, 'traffic': ncu_traffic(dominant), 'peak_source': hbm_src,
-                        'note': 'bytes are SURVEY 8(d) algorithmic bytes; the descent is a chain of dependent fp32 additions in the '
-                                'reference order (bit-exact parity), bounded by fp32-pipe issue and latency, not by HBM (DESIGN.md 5.1)'}
+        flops = net_flops(S, W, D) * n_desc
+        by_kernel = {}
+        for kind in ('descend_expand', 'net', 'backup'):
+            traffic, tnote = ncu_traffic(kind, args.config)
+            ms_k, n_k = split[kind], per_move_launches[kind]
+            hbm = bytes_by[kind] / (ms_k / 1e3) / 1e9
+            entry = {'bound': 'hbm', 'achieved': hbm, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm / hbm_peak, 'peak_source': hbm_src,
+                     'ms_per_move': ms_k, 'us_per_launch': ms_k * 1e3 / max(n_k, 1), 'algorithmic_bytes_per_launch': bytes_by[kind] / max(n_k, 1),
+                     'traffic': traffic, 'traffic_source': tnote}
+            if kind == 'net':
+                tf = flops / (ms_k / 1e3) / 1e12
+                entry.update({'bound': 'tensor', 'achieved': tf, 'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': tf / tc_peak,
+                              'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
+                              'hbm_gbs': hbm, 'note': 'useful fp32-equivalent FLOPs (SURVEY 8d); the kernel issues 3 fp16 MMAs per product (hi*hi + hi*lo + lo*hi) '
+                                                      'to reach fp32 accuracy, so the tensor pipe does 3x this work'})
+            by_kernel[kind] = entry
+        # the env transition (Hex.step) of the real worlds: one launch per move, timed on its own
+        by_kernel['hex_step'] = time_hex_step(play.worlds, hbm_peak, hbm_src)
+        roofline = dict(by_kernel[dominant])
+        roofline['kernel'] = {'descend_expand': 'descend + expand + env step (one launch per simulation)', 'net': 'fc_forward (leaf evaluation)',
+                              'backup': 'backup + q-range'}[dominant]
+        if dominant != 'net':
+            roofline['note'] = ('bytes are SURVEY 8(d) algorithmic bytes; the descent is a chain of dependent fp32 additions in the reference order '
+                                '(bit-exact parity), bounded by fp32-pipe issue and latency, not by HBM (DESIGN.md 5.1)')
+        roofline['by_kernel'] = by_kernel
         roofline['ms_per_move_by_kernel'] = {k: round(v, 3) for k, v in split.items()}
         roofline['launches_per_move_by_kernel'] = per_move_launches
         roofline['algorithmic_bytes_per_move'] = {k: int(v) for k, v in bytes_by.items()}
-        roofline['net_tflops'] = net_flops(S, W, D) * n_desc / (split['net'] / 1e3) / 1e12
+        roofline['net_tflops'] = flops / (split['net'] / 1e3) / 1e12
         roofline['tree_shape'] = {'policy_evals_per_descent': counters[0] / max(counters[3], 1),
                                   'children_per_eval': counters[1] / max(counters[0], 1),
                                   'newton_iters_per_eval': counters[2] / max(counters[0], 1)}
 
-        cpu = cpu_baseline(args.config, sd, steps=3, warmup=1) if (world == 1 and not args.no_cpu) else None
-        refcuda = reference_cuda_baseline(args.config, sd) if (world == 1 and not args.no_cpu) else None
+        # the CPU and reference-CUDA legs load oracle/ (and oracle/_ref): they run in their own processes, after the timed regions, so that
+        # this process — whose loaded libraries the driver records — holds the product library only
+        cpu = run_leg('cpu_baseline', args.config) if (world == 1 and not args.no_cpu) else None
+        refcuda = run_leg('reference_cuda', args.config) if (world == 1 and not args.no_cpu) else None
+        extra = run_extras(args) if (world == 1 and not args.no_extra) else None
         result = {
             'metric': 'MCTS sims/sec', 'value': value, 'unit': 'sims/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -324,6 +428,7 @@ def run_ours(args):
             'roofline': roofline,
             'cpu_baseline': cpu,
             'reference_cuda': refcuda,
+            'extra': extra,
         }
         if world > 1:
             result['config']['allgather_bytes_per_rank_per_move'] = B * record_width(A)
@@ -339,35 +444,58 @@ def run_ours(args):
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_baseline(config, sd, steps, warmup):
     import torch
-    from oracle import build_ref, pyref
+    from oracle import build_ref, pyref, refpy
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core it can, as a stand-alone reference process would
+    torch.set_num_threads(os.cpu_count() or 1)
     S, B, T, W, D = CONFIGS[config]
     Bc = min(CPU_SAMPLE_ENVS.get(config, 512 if S <= 9 else 128), B)
-    if build_ref.available('O0'):
-        ops, kind = pyref.RefOps('O0'), 'reference'
-    else:
-        ops, kind = pyref.COps(), 'port'
-    torch.manual_seed(0)
-    g = torch.Generator().manual_seed(0)
-    w = pyref.HexWorld.initial(Bc, S, ops)
-    for _ in range(2 * S * S):
-        w, _ = w.step(torch.multinomial(w.valid.float(), 1, generator=g).squeeze(-1))
-    net = pyref.FCNet(sd)
+    python = 'restated'
+    if build_ref.available('O0') and refpy.present():
+        # the reference's OWN Python (Hex, MCTSAgent, FCModel) on its own CPU kernels — only where /root/reference exists (not on the GPU box)
+        r = refpy.load('O0')
+        kind, python = 'reference', 'reference'
+        torch.manual_seed(0)
+        g = torch.Generator().manual_seed(0)
+        w = r.Hex.initial(Bc, S, device='cpu')
+        for _ in range(2 * S * S):
+            w, _ = w.step(torch.multinomial(w.valid.float(), 1, generator=g).squeeze(-1))
+        rnet = r.FCModel(w.obs_space, w.action_space, width=W, depth=D)
+        rnet.load_state_dict(sd)
+        ragent = r.MCTSAgent(rnet, n_nodes=T, c_puct=1 / 16)
 
-    def move(w):
-        d = pyref.agent_call(w, net, n_nodes=T, c_puct=1 / 16)
-        w2, _ = w.step(d.actions)
-        return w2
+        def move(w):
+            d = ragent(w)
+            w2, _ = w.step(d.actions)
+            return w2
+    else:
+        if build_ref.available('O0'):
+            ops, kind = pyref.RefOps('O0'), 'reference'
+        else:
+            ops, kind = pyref.COps(), 'port'
+        torch.manual_seed(0)
+        g = torch.Generator().manual_seed(0)
+        w = pyref.HexWorld.initial(Bc, S, ops)
+        for _ in range(2 * S * S):
+            w, _ = w.step(torch.multinomial(w.valid.float(), 1, generator=g).squeeze(-1))
+        net = pyref.FCNet(sd)
+
+        def move(w):
+            d = pyref.agent_call(w, net, n_nodes=T, c_puct=1 / 16)
+            w2, _ = w.step(d.actions)
+            return w2
     for _ in range(warmup):
         w = move(w)
     t0 = time.perf_counter()
     for _ in range(steps):
         w = move(w)
     dt = time.perf_counter() - t0
-    return {'value': Bc * T * steps / dt, 'unit': 'sims/s', 'cores': torch.get_num_threads(), 'kind': kind,
-            'host_cpus': os.cpu_count(), 'seconds': dt,
+    return {'value': Bc * T * steps / dt, 'unit': 'sims/s', 'cores': torch.get_num_threads(), 'kind': kind, 'python': python,
+            'host_cpus': os.cpu_count(), 'seconds': dt, 'sample_envs': Bc, 'warmup': warmup,
             'sample': f'{steps} moves of {Bc} envs (of {B}) at {describe(config)}; '
                       + ('reference CPU kernels built from its unmodified sources at the reference loader\'s flags (-O0), '
-                         'single-threaded per-env loops as in the reference, torch ops on all threads; Python orchestration restated (oracle/pyref.py)'
+                         'single-threaded per-env loops as in the reference, torch ops on all threads; '
+                         + ('the reference\'s own Python (Hex, MCTSAgent, FCModel) drives them'
+                            if python == 'reference' else 'Python orchestration restated (oracle/pyref.py): /root/reference is not on this machine')
                          if kind == 'reference' else 'C restatement of the reference kernels (oracle/boardlaw_oracle.c, -O2)')}
 
 
@@ -420,14 +548,16 @@ def run_reference(args):
     S, B, T, W, D = CONFIGS[args.config]
     sd = synthetic_state_dict(S, W, D, seed=0)
     t0 = time.perf_counter()
-    cpu = cpu_baseline(args.config, sd, steps=args.steps, warmup=min(args.warmup, 1))
+    # a bounded sample: at most 8 timed moves (~8 s each at c2) however many steps the GPU arm was asked for, same warm-up rule as ours
+    steps = min(args.steps, 8)
+    cpu = cpu_baseline(args.config, sd, steps=steps, warmup=min(max(args.warmup, 1), 3))
     Bc = CPU_SAMPLE_ENVS.get(args.config, 512)
     print(json.dumps({
         'impl': 'reference', 'metric': 'MCTS sims/sec', 'value': cpu['value'], 'unit': 'sims/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': cpu['seconds'] / args.steps * 1e3,
+        'steps': steps, 'warmup': cpu['warmup'], 'ms_per_step': cpu['seconds'] / steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'{args.config}: {describe(args.config)}', 'sample_envs': min(Bc, B), 'device': 'host CPU'},
-        'cpu_baseline': {k: cpu[k] for k in ('kind', 'cores', 'sample', 'value', 'unit', 'host_cpus')},
+        'cpu_baseline': {k: cpu[k] for k in ('kind', 'python', 'cores', 'sample', 'value', 'unit', 'host_cpus')},
         'e2e': {'value': cpu['value'], 'unit': 'sims/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
 
@@ -441,8 +571,16 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'amp'])
     ap.add_argument('--envs', type=int, default=0, help='override envs per GPU (debugging)')
-    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline / reference_cuda legs')
+    ap.add_argument('--no-extra', action='store_true', help='skip the other configs (c3, c5 sweep, c2 amp) reported under "extra"')
+    ap.add_argument('--leg', default=None, choices=['cpu_baseline', 'reference_cuda'], help='(internal) run one baseline leg and print its JSON')
     args = ap.parse_args()
+    if args.leg:
+        from boardlaw_b200.networks import synthetic_state_dict
+        S, B, T, W, D = CONFIGS[args.config]
+        sd = synthetic_state_dict(S, W, D, seed=0)
+        print(json.dumps(cpu_baseline(args.config, sd, steps=2, warmup=1) if args.leg == 'cpu_baseline' else reference_cuda_baseline(args.config, sd)))
+        return
     if args.impl == 'reference':
         run_reference(args)
     else:
