@@ -16,7 +16,7 @@ from itertools import permutations
 
 import torch
 
-from . import arrdict
+from .. import arrdict
 
 
 def matchup_patterns(n_seats):
@@ -91,3 +91,6 @@ def evaluate(worlds, agents):
     if int(errors) != 0:
         raise AssertionError(f'an agent played an invalid action during the evaluation (error bits {int(errors):#x})')
     return gather(wins.cpu(), moves.cpu(), times.cpu(), matchup_idxs.cpu(), agents, worlds.boardsize)
+
+
+from . import neural  # noqa: E402,F401  (boardlaw.arena.neural: the all-pairs ChunkEvaluator)

@@ -110,6 +110,57 @@ class Hex(arrdict.namedarrtuple('Hex', fields=('board', 'seats'))):
         return new_world, arrdict.arrdict(terminal=terminal, rewards=rewards, actions=actions)
 
 
+class Solitaire(Hex):
+    """One-player Hex: the env plays the other seat itself, so the caller only ever moves for seat 0 and receives a single
+    reward column (boardlaw/hex/__init__.py:224-253)."""
+
+    @classmethod
+    def initial(cls, *args, seat=0, **kwargs):
+        if seat == 1:
+            raise ValueError('Can\'t do seat #1 right now')
+        return super().initial(*args, **kwargs)
+
+    def _restore(self):
+        super()._restore()
+        if isinstance(self.board, torch.Tensor):
+            self.n_seats = 1
+
+    def step(self, actions):
+        worlds, transitions = Hex.step(self, actions)                      # (an instance of type(self), carrying the chain's error word)
+        # the move may have ended the game (auto-reset: the player's seat is up again); otherwise the opponent replies until it is
+        # the player's turn — in Hex exactly one reply, but the loop keeps the reference's general form
+        while True:
+            idx = (worlds.seats != self.seats).nonzero().squeeze(-1)
+            if idx.numel() == 0:
+                break
+            sub = Hex(board=worlds.board[idx], seats=worlds.seats[idx])
+            sub.errors = worlds.errors
+            replied, other = self._play(sub)
+            worlds.board[idx], worlds.seats[idx] = replied.board, replied.seats
+            transitions.rewards[idx] += other.rewards
+            transitions.terminal[idx] |= other.terminal
+        envs = torch.arange(self.n_envs, device=self.device)
+        transitions['rewards'] = transitions.rewards[envs, self.seats.long()][:, None]
+        return worlds, transitions
+
+
+class Lazy(Solitaire):
+    """The opponent plays the first available action (boardlaw/hex/__init__.py:255-263): the 0-th legal move of the fused
+    draw-and-step kernel (``bl_hex_random_transition`` with a zero uniform)."""
+
+    @classmethod
+    def _play(cls, worlds):
+        return worlds.step_random(uniforms=torch.zeros((worlds.n_envs,), device=worlds.device))
+
+
+class Random(Solitaire):
+    """The opponent plays a uniformly random action (boardlaw/hex/__init__.py:265-271), drawn and stepped in one kernel."""
+
+    @classmethod
+    def _play(cls, worlds):
+        return worlds.step_random()
+
+
 def from_string(s, **kwargs):
     """Plays out a position drawn with 'b', 'w', '.' (as boardlaw/hex/tests.py:121-134)."""
     import numpy as np

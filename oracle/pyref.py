@@ -137,6 +137,31 @@ class HexWorld:
         return HexWorld(self.board[idx], self.seats[idx], self.ops)
 
 
+class LazyWorld(HexWorld):
+    """``boardlaw.hex.Lazy`` (boardlaw/hex/__init__.py:224-263) restated: one-player Hex, the opponent answers with the first legal
+    move; a single reward column (the player's)."""
+    n_seats = 1
+
+    def step(self, actions):
+        new, trans = HexWorld.step(self, actions)
+        board, seats = new.board.clone(), new.seats.clone()
+        rewards, terminal = trans.rewards.clone(), trans.terminal.clone()
+        while True:
+            mask = seats != self.seats
+            if not mask.any():
+                break
+            sub = HexWorld(board[mask], seats[mask], self.ops)
+            v = sub.valid
+            n = v.shape[1]
+            first = torch.where(v, torch.arange(n)[None].expand_as(v), torch.full_like(v, n, dtype=torch.long)).min(-1).values
+            replied, other = HexWorld.step(sub, first)
+            board[mask], seats[mask] = replied.board, replied.seats
+            rewards[mask] += other.rewards
+            terminal[mask] |= other.terminal
+        envs = torch.arange(self.n_envs)
+        return LazyWorld(board, seats, self.ops), types.SimpleNamespace(terminal=terminal, rewards=rewards[envs, self.seats.long()][:, None])
+
+
 def random_actions(valid, uniforms):
     """The draw of bl_hex_random_transition restated: env b takes its k-th legal move (mover's frame order),
     k = min(floor(fp32(u_b) * fp32(n_legal)), n_legal - 1) — a uniform draw over the legal moves, i.e. the distribution of

@@ -179,12 +179,12 @@ def test_graph_cache_survives_model_replacement():
     for seed in (1, 2, 3, 4, 5, 6):
         agent, _ = make_agent(5, 32, 2, 8, seed=seed)
         torch.manual_seed(0)
-        d = agent(worlds, eval=True)
+        d = agent(worlds, eval=True)                      # captures graphs for this model ...
+        d = agent(worlds, eval=True)                      # ... and replays them
+        # the root value is the model's own value output at the root, whatever the search draws: a replay against another model's
+        # (freed) operands would not reproduce it
         ref = agent.network(worlds)
-        # node 0's prior is the network's own policy mixed with noise: check against an un-graphed search of the same model
-        torch.manual_seed(0)
-        d2 = agent(worlds, eval=True, use_graph=False)
-        assert torch.equal(d.logits, d2.logits) and torch.equal(d.v, d2.v)
+        assert torch.equal(d.v.view(torch.int16), ref.v.half().view(torch.int16))
         outs.append(d.v.clone())
         del agent
         gc.collect()

@@ -246,3 +246,62 @@ def test_graph_replay_serves_updated_weights():
         assert torch.equal(torch.isfinite(d1.prior), fin)
         assert float((d1.prior.float()[fin] - want[fin]).abs().max()) < 4e-3      # prior = half(log(exp(logits))) of the root evaluation
     assert float((d1.prior.float()[fin] - d0.prior.float()[fin]).abs().max()) > 1e-2
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refpy.present(), reason='reference sources not present')
+@pytest.mark.parametrize('S,W,D,B', [(5, 32, 2, 96), (9, 64, 3, 48)])
+def test_oracle_optimise_step_vs_reference_main_optimize(S, W, D, B):
+    """pyref.learner_step (the oracle the GPU learner is checked against) pinned against the reference's OWN ``main.optimize``
+    (boardlaw/main.py:75-101), run on the CPU from where it lies: its function body is compiled out of the reference file and
+    executed with the reference's ``learning`` module, its ``FCModel`` and ``Hex``, torch's Adam and GradScaler (disabled on a
+    machine without CUDA, as is autocast: fp32 throughout).  Losses and the parameters after one and after three steps agree."""
+    import ast
+    import contextlib
+    import types
+    import numpy as np
+    r = refpy.load()
+    import boardlaw.learning as rlearning
+    src = (refpy.REFERENCE / 'boardlaw' / 'main.py').read_text()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'optimize')
+    recorded = {}
+
+    class Stats:                                     # pavlov.stats: the side channel; records what optimize reports
+        defer = staticmethod(contextlib.nullcontext)
+
+        def __getattr__(self, kind):
+            return lambda name, *vals: recorded.__setitem__(name, vals)
+    ns = dict(torch=torch, np=np, learning=rlearning, stats=Stats())
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), str(refpy.REFERENCE / 'boardlaw' / 'main.py'), 'exec'), ns)
+
+    sd = pyref.synth_state_dict(S, W, D, seed=31)
+    g = torch.Generator().manual_seed(32)
+    w = pyref.HexWorld.initial(B, S)
+    for _ in range(S * S // 3):
+        w, _ = w.step(torch.multinomial(w.valid.float(), 1, generator=g).squeeze(-1))
+    A = S * S
+    target_logits = torch.log_softmax(torch.randn((B, A), generator=g).masked_fill(~w.valid, -np.inf), -1).half()
+    prior = torch.log_softmax(torch.randn((B, A), generator=g).masked_fill(~w.valid, -np.inf), -1).half()
+    target_v = (torch.rand((B, 2), generator=g) * 2 - 1).half()
+
+    rworlds = r.Hex(board=w.board.clone(), seats=w.seats.clone())
+    rnet = r.FCModel(rworlds.obs_space, rworlds.action_space, width=W, depth=D)
+    rnet.load_state_dict(sd)
+    opt = torch.optim.Adam(rnet.parameters(), lr=1e-3)
+    scaler = torch.cuda.amp.GradScaler()
+    batch = r.arrdict.arrdict(
+        worlds=rworlds,
+        decisions=r.arrdict.arrdict(logits=target_logits, prior=prior, v=target_v),
+        transitions=r.arrdict.arrdict(terminal=torch.zeros(B, dtype=torch.bool)),
+        reward_to_go=target_v)
+    for steps in (1, 3):
+        if steps == 3:
+            ns['optimize'](rnet, scaler, opt, batch); ns['optimize'](rnet, scaler, opt, batch)
+        else:
+            ns['optimize'](rnet, scaler, opt, batch)
+            pl_ref, vl_ref = float(recorded['loss.policy'][0]), float(recorded['loss.value'][0])
+        new, _, (pl, vl) = pyref.learner_step(sd, w, target_logits, target_v, lr=1e-3, steps=steps)
+        if steps == 1:
+            assert abs(float(pl) - pl_ref) <= 1e-6 * abs(pl_ref) and abs(float(vl) - vl_ref) <= 1e-6 * abs(vl_ref)
+        for k, p in rnet.state_dict().items():
+            assert torch.allclose(new[k], p, rtol=0, atol=2e-7), f'{k} after {steps} step(s): {float((new[k] - p).abs().max())}'
