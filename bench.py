@@ -311,7 +311,7 @@ def run_ours(args):
     clocks.__exit__()
     clocks.window(t_begin, t_end)
     ms = e0.elapsed_time(e1)
-    gpu_launches = eng.launches - launches0 + args.steps      # + the env transition kernel of worlds.step
+    gpu_launches = eng.launches - launches0                   # every kernel of the move, the env transition and the record packing included, is the engine's
     if world > 1:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

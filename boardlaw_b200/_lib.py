@@ -13,7 +13,7 @@ import torch
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / 'libboardlaw_b200.so'
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class FCParams(Structure):
@@ -65,6 +65,9 @@ SIGNATURES = {
     'bl_tree_eval_leaves': (c_int, [POINTER(Tree), POINTER(FCParams), c_int, P, P]),
     'bl_tree_eval_root': (c_int, [POINTER(Tree), POINTER(FCParams), P, P, P, P]),
     'bl_tree_root': (c_int, [POINTER(Tree), c_int, P, P, P, P, P]),
+    'bl_tree_root_act': (c_int, [POINTER(Tree), c_int, P, P, P, P, P, P, c_int, c_uint64, P]),
+    'bl_tree_set_root_prior': (c_int, [POINTER(Tree), P, P, P, P, P, c_float, c_float, c_uint64, P]),
+    'bl_pack_records': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     'bl_tree_children_dense': (c_int, [POINTER(Tree), P, P]),
     'bl_reward_to_go': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
     'bl_policy_value_loss': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, P]),

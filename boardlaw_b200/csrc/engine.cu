@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) reset_kernel(bl_tree t, const uint8_t *__
     for (long long i = i0; i < (long long)t.B * TP; i += stride) t.parent_of[i] = -1;
     for (long long i = i0; i < BT * ((t.T + 63) >> 6); i += stride) t.kids[i] = 0ull;
     for (long long i = i0; i < t.B; i += stride) t.c_puct[i] = c_puct;
+    if (i0 == 0) t.counters[C_MOVE] += 1;                       // keys this search's in-kernel random streams; no host write per move
     int *qr = reinterpret_cast<int *>(t.qrange);
     for (long long i = i0; i <= t.T; i += stride) {
         // slot 1 serves the first descent: the all-zero tree has (min,max) = (0,0)
@@ -54,26 +55,87 @@ __global__ void __launch_bounds__(256) reset_kernel(bl_tree t, const uint8_t *__
     }
 }
 
+// Gamma(shape) draw, Marsaglia & Tsang (2000) with the shape < 1 boost, on the counter-based Philox stream (key, ctr): the
+// in-kernel counterpart of torch._sample_dirichlet's gamma draws (same distribution, different stream)
+__device__ __forceinline__ float bl_gamma(float shape, uint64_t key, uint64_t ctr) {
+    const float a1 = shape < 1.f ? shape + 1.f : shape;
+    const float d = a1 - 1.f / 3.f, c = 1.f / sqrtf(9.f * d);
+    float g = d;
+    for (uint32_t attempt = 0; attempt < 64; attempt++) {
+        const bl_philox_out o = bl_philox(key, ctr, attempt);
+        const float u1 = ((float)(o.x >> 8) + .5f) * (1.f / 16777216.f), u2 = ((float)(o.y >> 8) + .5f) * (1.f / 16777216.f);
+        const float u3 = ((float)(o.z >> 8) + .5f) * (1.f / 16777216.f), u4 = ((float)(o.w >> 8) + .5f) * (1.f / 16777216.f);
+        const float x = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);                 // standard normal (Box-Muller)
+        const float v = (1.f + c * x) * (1.f + c * x) * (1.f + c * x);
+        if (v > 0.f && logf(u3) < .5f * x * x + d - d * v + d * logf(v)) {
+            g = d * v;
+            if (shape < 1.f) g *= powf(u4, 1.f / shape);
+            break;
+        }
+    }
+    return g;
+}
+
+struct PriorMix {                 // SRC == 2: what the root prior is mixed from (dirichlet_noise, boardlaw/mcts/__init__.py:13-24)
+    const uint8_t *board;         // (B,A) absolute-frame root boards
+    const int32_t *seats;         // (B,)
+    const float *draw;            // (B,A) injected raw Dirichlet sample (before masking), or NULL: drawn here
+    float eps, conc;              // noise_eps, alpha_scale / A
+    uint64_t seed;
+};
+
 // logits/v of one node per env -> pi row + row summary (+ prior when node 0) + v, rounding through half like
-// decisions.half() (boardlaw/mcts/__init__.py:135-136).  One warp per env.
-template <bool HALF_IN>
+// decisions.half() (boardlaw/mcts/__init__.py:135-136).  One warp per env.  SRC: 0 = fp32 rows, 1 = half rows, 2 = fp32 root rows
+// mixed with Dirichlet noise on the way in (MCTS.initialize, boardlaw/mcts/__init__.py:72-80).
+template <int SRC>
 __global__ void __launch_bounds__(256) set_eval_kernel(bl_tree t, int node, const void *__restrict__ logits_,
-                                                       const void *__restrict__ v_) {
+                                                       const void *__restrict__ v_, PriorMix mix) {
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int MAXK = 8;                                     // actions per lane (A <= 255)
     for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < t.B; b += nwarps) {
         const int nd = node >= 0 ? node : t.leaf[b];
         if (nd < 0) continue;
         const size_t slot = (size_t)b * t.T + nd;
+        float noise[MAXK];
+        if (SRC == 2) {
+            // the Dirichlet sample restricted to the legal moves and renormalised (draw[~valid] = 0; draw /= draw.sum())
+            const int seat = mix.seats[b], S = t.S;
+            const uint64_t move = t.counters[C_MOVE];
+            float tot = 0.f;
+#pragma unroll
+            for (int k = 0; k < MAXK; k++) {
+                const int a = lane + 32 * k;
+                float g = 0.f;
+                if (a < t.A) {
+                    const int cell = seat ? (a % S) * S + a / S : a;                  // white sees the transposed board
+                    if (mix.board[(size_t)b * t.A + cell] == 0)
+                        g = mix.draw ? mix.draw[(size_t)b * t.A + a]
+                                     : fmaxf(bl_gamma(mix.conc, mix.seed ^ (move * 0xD1B54A32D192ED03ull), ((uint64_t)b << 8) | (uint64_t)a), 1.17549435e-38f);
+                }
+                noise[k] = g;
+                tot += g;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+#pragma unroll
+            for (int k = 0; k < MAXK; k++) noise[k] = noise[k] / tot;
+        }
         float mx = 0.f, mn = BL_INF, pa = 0.f;
         int fz = 255, lz = -1;
         double carry = 0.;                                     // running prefix sum of the row (cpi), chunk of 32 actions at a time
-        for (int a0 = 0; a0 < t.AP; a0 += 32) {
+#pragma unroll
+        for (int k = 0; k < MAXK; k++) {
+            const int a0 = 32 * k;
+            if (a0 >= t.AP) break;
             const int a = a0 + lane;
             float p = 0.f;
             if (a < t.A) {
                 const size_t i = (size_t)b * t.A + a;
-                const bl_half h = HALF_IN ? reinterpret_cast<const bl_half *>(logits_)[i] : bl_f2h(reinterpret_cast<const float *>(logits_)[i]);
+                bl_half h;
+                if (SRC == 1) h = reinterpret_cast<const bl_half *>(logits_)[i];
+                else if (SRC == 0) h = bl_f2h(reinterpret_cast<const float *>(logits_)[i]);
+                else h = bl_f2h(logf(expf(reinterpret_cast<const float *>(logits_)[i]) * (1.f - mix.eps) + noise[k] * mix.eps));
                 p = t.exp_lut[h];
                 t.pi[slot * t.AP + a] = p;
                 if (nd == 0) t.prior[i] = h;
@@ -81,15 +143,17 @@ __global__ void __launch_bounds__(256) set_eval_kernel(bl_tree t, int node, cons
                 if (p != 0.f) { mx = fmaxf(mx, p); mn = fminf(mn, p); fz = min(fz, a); lz = max(lz, a); }
                 pa = __fmaf_rn((float)a, p, pa);
             }
-            double run = (double)p;
+            if (t.cpi) {
+                double run = (double)p;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double up = __shfl_up_sync(0xffffffffu, run, o);
-                if (lane >= o) run += up;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double up = __shfl_up_sync(0xffffffffu, run, o);
+                    if (lane >= o) run += up;
+                }
+                run += carry;
+                if (a < t.AP) t.cpi[slot * t.AP + a] = (float)run;
+                carry = __shfl_sync(0xffffffffu, run, 31);
             }
-            run += carry;
-            if (t.cpi && a < t.AP) t.cpi[slot * t.AP + a] = (float)run;
-            carry = __shfl_sync(0xffffffffu, run, 31);
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) pa += __shfl_xor_sync(0xffffffffu, pa, o);
@@ -104,7 +168,7 @@ __global__ void __launch_bounds__(256) set_eval_kernel(bl_tree t, int node, cons
         if (lane == 0) {
             bl_half hv[2];
             for (int s = 0; s < 2; s++)
-                hv[s] = HALF_IN ? reinterpret_cast<const bl_half *>(v_)[(size_t)b * 2 + s] : bl_f2h(reinterpret_cast<const float *>(v_)[(size_t)b * 2 + s]);
+                hv[s] = SRC == 1 ? reinterpret_cast<const bl_half *>(v_)[(size_t)b * 2 + s] : bl_f2h(reinterpret_cast<const float *>(v_)[(size_t)b * 2 + s]);
             uint32_t *ax = reinterpret_cast<uint32_t *>(t.aux + slot);
             ax[1] = (uint32_t)hv[0] | ((uint32_t)hv[1] << 16);
             if (node < 0) reinterpret_cast<uint32_t *>(t.leaf_v)[b] = ax[1];
@@ -294,7 +358,8 @@ __global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int si
 // ---- root ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ENT) root_kernel(bl_tree t, int sim, const bl_half *__restrict__ log_lut,
                                                    bl_half *__restrict__ logits, bl_half *__restrict__ v,
-                                                   int64_t *__restrict__ n_leaves) {
+                                                   int64_t *__restrict__ n_leaves, int64_t *__restrict__ actions,
+                                                   const float *__restrict__ uniforms, int greedy, uint64_t seed) {
     extern __shared__ __align__(16) uint8_t raw[];
     Smem sm = carve(raw, t.A);
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
@@ -329,8 +394,34 @@ __global__ void __launch_bounds__(ENT) root_kernel(bl_tree t, int sim, const bl_
     int it;
     const float alpha = bl_newton(top, q, FP, A, &it);
     // probs -> half -> log -> half (MCTS.root, boardlaw/mcts/__init__.py:142-149); log through the host-libm table
-    for (int a = 0; a < A; a++)
-        logits[(size_t)b * A + a] = log_lut[bl_f2h(bl_prob(top[a * FP], q[a * FP], alpha))];
+    float tot = 0.f, best = -BL_INF;
+    int arg = -1;
+    for (int a = 0; a < A; a++) {
+        const bl_half h = log_lut[bl_f2h(bl_prob(top[a * FP], q[a * FP], alpha))];
+        logits[(size_t)b * A + a] = h;
+        if (actions) {
+            // MCTSAgent.__call__ (boardlaw/mcts/__init__.py:220-221): argmax of the root policy, or a draw from Categorical(logits)
+            const float l = bl_h2f(h), w = expf(l);
+            top[a * FP] = w;                                    // (the row is dead: keep the weights for the draw)
+            tot += w;
+            if (l > best) { best = l; arg = a; }
+        }
+    }
+    if (actions) {
+        int act = arg;
+        if (!greedy) {
+            const float u = uniforms ? uniforms[b] : ((float)(bl_philox(seed ^ (t.counters[C_MOVE] * 0x9E3779B97F4A7C15ull), (uint64_t)b, 0xAC71ull).x >> 8) + .5f) * (1.f / 16777216.f);
+            const float target = u * tot;
+            float cum = 0.f;
+            act = -1;
+            for (int a = 0; a < A; a++) {
+                const float w = top[a * FP];
+                cum += w;
+                if (w > 0.f) { act = a; if (cum >= target) break; }
+            }
+        }
+        actions[b] = act;
+    }
     const bl_aux ra = bl_ld_aux(t.aux + node0);
     for (int s = 0; s < Sn; s++) v[(size_t)b * Sn + s] = ra.v[s];
     int leaves = 0;
@@ -405,8 +496,18 @@ extern "C" int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, 
     if (t->B == 0) return 0;
     if (node >= t->T) return -1;
     int grid = grid1d((long long)t->B * 32, 256);            // one warp per env
-    if (inputs_are_half) set_eval_kernel<true><<<grid, 256, 0, bl_cu(stream)>>>(*t, node, logits, v);
-    else set_eval_kernel<false><<<grid, 256, 0, bl_cu(stream)>>>(*t, node, logits, v);
+    const PriorMix none = {nullptr, nullptr, nullptr, 0.f, 0.f, 0ull};
+    if (inputs_are_half) set_eval_kernel<1><<<grid, 256, 0, bl_cu(stream)>>>(*t, node, logits, v, none);
+    else set_eval_kernel<0><<<grid, 256, 0, bl_cu(stream)>>>(*t, node, logits, v, none);
+    BL_LAUNCH_CHECK();
+}
+
+extern "C" int bl_tree_set_root_prior(const bl_tree *t, const float *logits, const float *v, const uint8_t *board, const int32_t *seats,
+                                      const float *draw, float noise_eps, float alpha_scale, uint64_t seed, bl_stream stream) {
+    if (int e = check_tree(t)) return e;
+    if (t->B == 0) return 0;
+    const PriorMix mix = {board, seats, draw, noise_eps, alpha_scale / (float)t->A, seed};
+    set_eval_kernel<2><<<grid1d((long long)t->B * 32, 256), 256, 0, bl_cu(stream)>>>(*t, 0, logits, v, mix);
     BL_LAUNCH_CHECK();
 }
 
@@ -522,6 +623,56 @@ extern "C" int bl_tree_eval_root(const bl_tree *t, const bl_fc_params *p, float 
     return bl_fc_forward(p, s.board, s.seats, logits, v, s.net, t->B, stream);
 }
 
+extern "C" int bl_tree_root_act(const bl_tree *t, int sim, const bl_half *log_lut, bl_half *logits, bl_half *v, int64_t *n_leaves,
+                                int64_t *actions, const float *uniforms, int greedy, uint64_t seed, bl_stream stream) {
+    if (int e = check_tree(t)) return e;
+    if (t->B == 0) return 0;
+    if (sim < 1 || sim > t->T || !actions) return -1;
+    size_t smem = descend_smem(t->A);
+    if (smem > 227 * 1024) return -2;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    root_kernel<<<(t->B + ENT - 1) / ENT, ENT, smem, bl_cu(stream)>>>(*t, sim, log_lut, logits, v, n_leaves, actions, uniforms, greedy, seed);
+    BL_LAUNCH_CHECK();
+}
+
+// One (B, R) uint8 trajectory record per env for the move just played — the row selfplay.pack_records assembles with eight torch
+// casts and two concatenations: board A u8 | seat u8 | terminal u8 | action i16 | rewards 2 x f16 | v 2 x f16 | logits A x f16 |
+// prior A x f16 | zero padding to R (a multiple of 16).  One warp per env, byte-granular (the fields are not aligned).
+__global__ void __launch_bounds__(256) pack_records_kernel(const uint8_t *__restrict__ board, const int32_t *__restrict__ seats, const uint8_t *__restrict__ terminal,
+                                                           const int64_t *__restrict__ actions, const float *__restrict__ rewards, const bl_half *__restrict__ v,
+                                                           const bl_half *__restrict__ logits, const bl_half *__restrict__ prior, uint8_t *__restrict__ rec,
+                                                           int B, int A, int R) {
+    const int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += nwarps) {
+        const uint16_t act = (uint16_t)(int16_t)actions[b];
+        const bl_half r0 = bl_f2h(rewards[2 * b]), r1 = bl_f2h(rewards[2 * b + 1]);
+        for (int o = lane; o < R; o += 32) {
+            uint8_t x = 0;
+            int f = o;
+            if (f < A) x = board[(size_t)b * A + f];
+            else if ((f -= A) == 0) x = (uint8_t)seats[b];
+            else if (f == 1) x = terminal[b];
+            else if (f < 4) x = (uint8_t)(act >> (8 * (f - 2)));
+            else if (f < 8) x = (uint8_t)((f < 6 ? r0 : r1) >> (8 * (f & 1)));
+            else if (f < 12) x = (uint8_t)(v[2 * b + ((f - 8) >> 1)] >> (8 * (f & 1)));
+            else if ((f -= 12) < 2 * A) x = (uint8_t)(logits[(size_t)b * A + (f >> 1)] >> (8 * (f & 1)));
+            else if ((f -= 2 * A) < 2 * A) x = (uint8_t)(prior[(size_t)b * A + (f >> 1)] >> (8 * (f & 1)));
+            rec[(size_t)b * R + o] = x;
+        }
+    }
+}
+
+extern "C" int bl_pack_records(const uint8_t *board, const int32_t *seats, const uint8_t *terminal, const int64_t *actions, const float *rewards,
+                               const bl_half *v, const bl_half *logits, const bl_half *prior, uint8_t *records, int B, int A, int R, bl_stream stream) {
+    if (B == 0) return 0;
+    if (R < 5 * A + 12) return -1;
+    pack_records_kernel<<<grid1d((long long)B * 32, 256), 256, 0, bl_cu(stream)>>>(board, seats, terminal, actions, rewards, v, logits, prior, records, B, A, R);
+    BL_LAUNCH_CHECK();
+}
+
 extern "C" int bl_tree_root(const bl_tree *t, int sim, const bl_half *log_lut, bl_half *logits, bl_half *v,
                             int64_t *n_leaves, bl_stream stream) {
     if (int e = check_tree(t)) return e;
@@ -533,7 +684,7 @@ extern "C" int bl_tree_root(const bl_tree *t, int sim, const bl_half *log_lut, b
         cudaError_t e = cudaFuncSetAttribute(root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    root_kernel<<<(t->B + ENT - 1) / ENT, ENT, smem, bl_cu(stream)>>>(*t, sim, log_lut, logits, v, n_leaves);
+    root_kernel<<<(t->B + ENT - 1) / ENT, ENT, smem, bl_cu(stream)>>>(*t, sim, log_lut, logits, v, n_leaves, nullptr, nullptr, 0, 0ull);
     BL_LAUNCH_CHECK();
 }
 

@@ -4,7 +4,7 @@
 
 #include "common.cuh"
 
-extern "C" int bl_abi_version(void) { return 8; }
+extern "C" int bl_abi_version(void) { return 9; }
 
 // The library links the CUDA runtime statically, so it carries its own "current device"; the host
 // wrapper calls this with the device index of the tensors before launching (the reference does the

@@ -77,6 +77,16 @@ class SearchEngine:
         self.out_logits = z((B, A), torch.float16)
         self.out_v = z((B, 2), torch.float16)
         self.out_n_leaves = z((B,), torch.int64)
+        # whole-move outputs (``play``): the agent's actions, the stepped worlds, the transition, the packed trajectory record
+        self.out_actions = z((B,), torch.int64)
+        self.nx_board = z((B, self.S, self.S), torch.uint8)
+        self.nx_seats = z((B,), torch.int32)
+        self.out_rewards = z((B, 2), torch.float32)
+        self.out_terminal = z((B,), torch.bool)
+        self.record_width = (5 * A + 12 + 15) // 16 * 16
+        self.out_record = z((B, self.record_width), torch.uint8)
+        self.errors = z((), torch.int32)              # rule violations of every env transition played through ``play``
+        self.n_sims = torch.full((B,), n_nodes + 1, dtype=torch.int64, device=dev)
         self._scratch = None
         self._scratch_key = None
         self._graphs = {}
@@ -95,9 +105,9 @@ class SearchEngine:
         self._graph_lru.append(key)
         while len(self._graph_lru) > self.MAX_GRAPH_KEYS:
             old = self._graph_lru.pop(0)
-            for part in ('head', 'sims'):
-                self._graphs.pop((part,) + old, None)
-                self._graph_launches.pop((part,) + old, None)
+            for k in [k for k in self._graphs if k[-len(old):] == old]:
+                self._graphs.pop(k, None)
+                self._graph_launches.pop(k, None)
             self._graph_refs.pop(old, None)
 
     def release(self):
@@ -168,6 +178,86 @@ class SearchEngine:
         self.launches += 1
         return self.out_logits, self.out_v, self.out_n_leaves
 
+    def set_root_prior(self, noise_eps, alpha_scale, draw=None):
+        """Node 0's evaluation = the root evaluation mixed with Dirichlet noise, in one launch (the draw injected, or in-kernel)."""
+        if draw is not None:
+            draw = draw.to(self.device, torch.float32).contiguous()
+            assert draw.shape == (self.B, self.A)
+        check(_lib.lib().bl_tree_set_root_prior(self._tp, ptr(self.root_logits), ptr(self.root_v), ptr(self.in_board), ptr(self.in_seats),
+                                                ptr(draw), float(noise_eps), float(alpha_scale), self.seed, self._stream()), 'bl_tree_set_root_prior')
+        self.launches += 1
+        self.sim = 1
+
+    def root_act(self, sim=None, greedy=False, uniforms=None):
+        """``root`` plus the agent's action per env (argmax when ``greedy``, else a draw from the root policy)."""
+        sim = self.sim if sim is None else sim
+        if uniforms is not None:
+            uniforms = uniforms.to(self.device, torch.float32).contiguous()
+        check(_lib.lib().bl_tree_root_act(self._tp, sim, ptr(self.log_lut), ptr(self.out_logits), ptr(self.out_v), ptr(self.out_n_leaves),
+                                          ptr(self.out_actions), ptr(uniforms), int(bool(greedy)), self.seed, self._stream()), 'bl_tree_root_act')
+        self.launches += 1
+        return self.out_logits, self.out_v, self.out_n_leaves, self.out_actions
+
+    def step_and_record(self, record=True):
+        """The env transition of the searched worlds under ``out_actions`` and the packed trajectory record of the move."""
+        l = _lib.lib()
+        check(l.bl_hex_transition(ptr(self.in_board), ptr(self.in_seats), ptr(self.out_actions), ptr(self.nx_board), ptr(self.nx_seats),
+                                  ptr(self.out_rewards), ptr(self.out_terminal), ptr(self.errors), 1, self.B, self.S, self._stream()), 'bl_hex_transition')
+        self.launches += 1
+        if record:
+            check(l.bl_pack_records(ptr(self.in_board), ptr(self.in_seats), ptr(self.out_terminal), ptr(self.out_actions), ptr(self.out_rewards),
+                                    ptr(self.out_v), ptr(self.out_logits), ptr(self.ws.prior), ptr(self.out_record), self.B, self.A,
+                                    self.record_width, self._stream()), 'bl_pack_records')
+            self.launches += 1
+
+    def _move_body(self, cparams, c_puct, noise_eps, alpha_scale, greedy, record):
+        self._reset(c_puct)
+        self.eval_root(cparams)
+        self.set_root_prior(noise_eps, alpha_scale)
+        for sim in range(1, self.T):
+            self.descend_expand(sim)
+            self.eval_leaves(cparams, sim)
+            self.backup(sim)
+        self.root_act(self.T, greedy)
+        self.step_and_record(record)
+
+    def play(self, board, seats, network, c_puct=1 / 16, noise_eps=.25, alpha_scale=10, greedy=False, record=True, use_graph=True):
+        """One whole MOVE of every env in ONE CUDA graph: MCTS.__init__ + initialize with in-kernel Dirichlet noise,
+        (n_nodes-1) x simulate, root, the agent's action (boardlaw/mcts/__init__.py:216-229), the env transition (boardlaw/main.py:177)
+        and the packed trajectory record (boardlaw/main.py:179) — every launch from libboardlaw_b200.so; the host copies the worlds in
+        and replays.  Returns views of static buffers, valid until the next call: (logits, prior, v, n_leaves, actions, new_board,
+        new_seats, rewards, terminal, record)."""
+        if board.shape[0] != self.B:
+            raise ValueError(f'{board.shape[0]} envs do not fit a workspace of {self.B} (play() runs whole batches only)')
+        cparams = network.packed()
+        self.in_board.copy_(board)
+        self.in_seats.copy_(seats)
+        self.move += 1
+        key = (cparams.W, cparams.D, cparams.precision, float(c_puct), network.token, network._pack_gen)
+        self._graph_refs[key] = network._pack
+        self._touch(key)
+        gkey = ('move', float(noise_eps), float(alpha_scale), bool(greedy), bool(record)) + key
+        if not use_graph:
+            self._move_body(cparams, c_puct, noise_eps, alpha_scale, greedy, record)
+        else:
+            g = self._graphs.get(gkey)
+            if g is None:
+                self._move_body(cparams, c_puct, noise_eps, alpha_scale, greedy, record)        # warm-up: kernel attributes, allocations
+                g = torch.cuda.CUDAGraph()
+                before = self.launches
+                with torch.cuda.graph(g):
+                    self._move_body(cparams, c_puct, noise_eps, alpha_scale, greedy, record)
+                self._graph_launches[gkey] = self.launches - before
+                self.launches = before
+                self._graphs[gkey] = g
+                self.in_board.copy_(board)                   # (the warm-up and the capture leave the inputs as they were; be explicit)
+                self.in_seats.copy_(seats)
+            g.replay()
+            self.launches += self._graph_launches[gkey]
+        self.sim = self.T
+        return (self.out_logits, self.ws.prior[:self.B], self.out_v, self.out_n_leaves, self.out_actions, self.nx_board, self.nx_seats,
+                self.out_rewards, self.out_terminal, self.out_record)
+
     def children_dense(self):
         out = torch.empty((self.B, self.T, self.A), dtype=torch.int16, device=self.device)
         check(_lib.lib().bl_tree_children_dense(self._tp, ptr(out), self._stream()), 'bl_tree_children_dense')
@@ -188,7 +278,8 @@ class SearchEngine:
             self.backup(sim)
         self.root(last)
 
-    _STATIC = ('in_board', 'in_seats', 'root_logits', 'root_v', 'out_logits', 'out_v', 'out_n_leaves')
+    _STATIC = ('in_board', 'in_seats', 'root_logits', 'root_v', 'out_logits', 'out_v', 'out_n_leaves', 'out_actions', 'nx_board', 'nx_seats',
+               'out_rewards', 'out_terminal', 'out_record', 'n_sims')
 
     def _search_partial(self, board, seats, network, **kwargs):
         """A search over n < capacity envs in the same workspace (arena-style callers, boardlaw/arena/common.py:86-96, hand
@@ -221,8 +312,7 @@ class SearchEngine:
         cparams = network.packed()
         self.in_board.copy_(board)
         self.in_seats.copy_(seats)
-        self.ws.counters[6:7].fill_(self.move)       # keys the in-kernel random stream of this move
-        self.move += 1
+        self.move += 1                                 # (the device-side move counter, counters[6], is advanced by the reset kernel)
         # graphs bake in the addresses of the network's staged operands: key on the model's own token (CPython reuses id() values once a
         # model is collected) and on the staging generation, and keep the operands alive for as long as the graph is cached
         key = (cparams.W, cparams.D, cparams.precision, float(c_puct), network.token, network._pack_gen)

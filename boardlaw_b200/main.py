@@ -42,9 +42,9 @@ def run(boardsize, width, depth, nodes=64, c_puct=1 / 16, lr=1e-3, n_envs=32 * 1
     records, losses = [], []
     for step in range(max_steps):
         while len(records) < buffer_len:                                            # main.py:173-185
-            decisions = agent(worlds, value=True)
-            new_worlds, transition = worlds.step(decisions.actions)
-            pool.gather(selfplay.pack_records(worlds, decisions, transition))
+            pool.sync_before_overwrite()
+            decisions, new_worlds, transition, rec = agent.play(worlds, record=True)      # the whole move: one captured graph
+            pool.gather(rec if rec is not None else selfplay.pack_records(worlds, decisions, transition))
             records.append(pool.wait().clone())
             worlds = new_worlds
         worlds.check()                                                              # rule violations recorded on the device by Hex.step

@@ -229,6 +229,29 @@ class MCTSAgent:
             v=r.v,
             actions=actions).clone()
 
+    def play(self, world, eval=False, record=False, **kwargs):
+        """One whole move — ``decisions = agent(world)`` and ``world.step(decisions.actions)`` — as ONE captured CUDA graph on the
+        fused engine (``SearchEngine.play``): in-kernel Dirichlet noise, search, action, env transition and, with ``record``, the packed
+        trajectory record.  Returns (decisions, new_world, transitions[, record]) as VIEWS of the engine's static buffers, valid
+        until the next call (clone what must outlive it).  Falls back to the two separate calls for worlds / networks the engine does
+        not take."""
+        from ..hex import Hex
+        kw = {**self.kwargs, **kwargs}
+        n_nodes = kw.get('n_nodes', 64)
+        if not (_fusable(world, self.network) and type(world) is Hex and 1 < n_nodes <= 32767):
+            d = self(world, eval=eval, **kwargs)
+            new_world, transitions = world.step(d.actions)
+            return (d, new_world, transitions, None) if record else (d, new_world, transitions)
+        eng = engine_for(world, n_nodes, kw.get('engine_seed', 0))
+        logits, prior, v, n_leaves, actions, nb, ns, rewards, terminal, rec = eng.play(
+            world.board, world.seats, self.network, c_puct=kw.get('c_puct', 1 / 16), noise_eps=kw.get('noise_eps', .25),
+            alpha_scale=kw.get('alpha_scale', 10), greedy=eval, record=record)
+        decisions = arrdict.arrdict(logits=logits, prior=prior, n_sims=eng.n_sims, n_leaves=n_leaves, v=v, actions=actions)
+        new_world = Hex(board=nb, seats=ns)
+        new_world.errors = eng.errors
+        transitions = arrdict.arrdict(terminal=terminal, rewards=rewards)
+        return (decisions, new_world, transitions, rec) if record else (decisions, new_world, transitions)
+
     def load_state_dict(self, sd):
         network = {k[8:]: v for k, v in sd.items() if k.startswith('network.')}
         kwargs = {k[7:]: v for k, v in sd.items() if k.startswith('kwargs.')}

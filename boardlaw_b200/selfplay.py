@@ -96,6 +96,12 @@ class TrajectoryPool:
                 out = torch.stack(parts)
             self._pending = (out, None)
 
+    def sync_before_overwrite(self):
+        """Orders the current stream after the gather in flight: call before re-using the buffer that was handed to ``gather`` (the
+        engine's static record buffer is rewritten by the next move)."""
+        if self._pending is not None and self._pending[1] is not None:
+            torch.cuda.current_stream(self._pending[0].device).wait_stream(self._pending[1])
+
     def wait(self):
         """(world, B, R) records of the last gathered move, safe to read on the current stream."""
         out, side = self._pending
@@ -113,10 +119,21 @@ class SelfPlay:
         self.pool = pool
 
     def step(self):
-        decisions = self.agent(self.worlds, value=True)
-        new_worlds, transitions = self.worlds.step(decisions.actions)
-        if self.pool is not None:
-            self.pool.gather(pack_records(self.worlds, decisions, transitions))
+        """One move of every env.  With an agent that has ``play`` (MCTSAgent on the fused engine) the whole move — search, action,
+        env transition, trajectory record — is one captured CUDA graph; what comes back are views of the engine's static buffers,
+        valid until the next step."""
+        if hasattr(self.agent, 'play'):
+            if self.pool is not None:
+                self.pool.sync_before_overwrite()          # the previous move's record is still being gathered on the side stream
+                decisions, new_worlds, transitions, rec = self.agent.play(self.worlds, record=True)
+                self.pool.gather(rec if rec is not None else pack_records(self.worlds, decisions, transitions))
+            else:
+                decisions, new_worlds, transitions = self.agent.play(self.worlds)
+        else:
+            decisions = self.agent(self.worlds, value=True)
+            new_worlds, transitions = self.worlds.step(decisions.actions)
+            if self.pool is not None:
+                self.pool.gather(pack_records(self.worlds, decisions, transitions))
         self.worlds = new_worlds
         return decisions, transitions
 

@@ -223,7 +223,7 @@ typedef struct bl_tree {
 int64_t bl_tree_scratch_bytes(const bl_tree *t);
 
 /* Resets the workspace for a new search rooted at (board (B,S,S) u8, seats (B,) i32).  The in-kernel random
- * stream is keyed by (seed, counters[6]); the host stores the move index in counters[6] before each search. */
+ * stream is keyed by (seed, counters[6]); the reset increments counters[6], the move index, itself (no host write per move). */
 int bl_tree_reset(const bl_tree *t, const uint8_t *board, const int32_t *seats, float c_puct,
                   bl_stream stream);
 
@@ -232,6 +232,15 @@ int bl_tree_reset(const bl_tree *t, const uint8_t *board, const int32_t *seats, 
  * and stored as pi = exp_lut[half(logit)].  node < 0 means "the current leaf of each env" (t->leaf). */
 int bl_tree_set_eval(const bl_tree *t, int node, const void *logits, const void *v,
                      int inputs_are_half, bl_stream stream);
+
+/* MCTS.initialize's second half in one launch (boardlaw/mcts/__init__.py:72-80 with dirichlet_noise, :13-24): the root evaluation
+ * (logits f32 (B,A) as bl_tree_eval_root returns them, v f32 (B,2)) is mixed in probability space with Dirichlet(alpha_scale/A) noise
+ * restricted to the legal moves of (board (B,S,S) u8, seats (B,) i32) and renormalised, log(exp(l)(1-eps) + d eps), and stored as node
+ * 0's evaluation exactly as bl_tree_set_eval(node=0) would.  draw: (B,A) f32 raw Dirichlet sample to use (the value
+ * torch.distributions.Dirichlet.sample returns, before masking), or NULL to draw the gammas in-kernel (Marsaglia-Tsang on Philox
+ * keyed by (seed, move counter, env, action)). */
+int bl_tree_set_root_prior(const bl_tree *t, const float *logits, const float *v, const uint8_t *board, const int32_t *seats,
+                           const float *draw, float noise_eps, float alpha_scale, uint64_t seed, bl_stream stream);
 
 /* descend + expand + env step of simulation `sim` (boardlaw/mcts/__init__.py:108-129): writes
  * t->leaf / leaf_parent / leaf_action, links new nodes, steps the parent's board into the leaf slot, records
@@ -291,6 +300,19 @@ int bl_tree_eval_root(const bl_tree *t, const bl_fc_params *p, float *logits, fl
  * `r.float().log().half()` (boardlaw/mcts/__init__.py:147). */
 int bl_tree_root(const bl_tree *t, int sim, const bl_half *log_lut, bl_half *logits, bl_half *v,
                  int64_t *n_leaves, bl_stream stream);
+
+/* bl_tree_root plus the agent's move (MCTSAgent.__call__, boardlaw/mcts/__init__.py:216-229): actions (B,) i64 = argmax of the root
+ * policy when greedy != 0 (eval=True), else a draw from Categorical(logits) by inverse CDF over exp(half logits) with uniforms (B,)
+ * f32 in [0,1) supplied by the caller, or drawn in-kernel from Philox keyed by (seed, move counter, env) when NULL. */
+int bl_tree_root_act(const bl_tree *t, int sim, const bl_half *log_lut, bl_half *logits, bl_half *v, int64_t *n_leaves,
+                     int64_t *actions, const float *uniforms, int greedy, uint64_t seed, bl_stream stream);
+
+/* The trajectory record of one move for every env — what the actor appends to its buffer (boardlaw/main.py:179:
+ * arrdict(worlds, decisions.half(), transitions)) — packed for the per-move all-gather: records (B,R) u8, R a multiple of 16 >= 5A+12:
+ * board A u8 | seat u8 | terminal u8 | action i16 | rewards 2 x f16 | v 2 x f16 | logits A x f16 | prior A x f16 | zero padding.
+ * board (B,A) u8 and seats (B,) i32 are the worlds the agent moved in; terminal (B,) u8, rewards (B,2) f32 the transition's. */
+int bl_pack_records(const uint8_t *board, const int32_t *seats, const uint8_t *terminal, const int64_t *actions, const float *rewards,
+                    const bl_half *v, const bl_half *logits, const bl_half *prior, uint8_t *records, int B, int A, int R, bl_stream stream);
 
 /* Materialises the reference's dense children (B,T,A) i16 tensor from the child lists. */
 int bl_tree_children_dense(const bl_tree *t, int16_t *children, bl_stream stream);
