@@ -160,14 +160,14 @@ def kernel_split(agent, worlds, T, n_moves=2):
             a.record(); fn(); b.record()
             pairs.append((kind, a, b))
         timed('other', lambda: (eng.reset(worlds.board, worlds.seats, 1 / 16), eng.eval_root(cp)))
-        timed('other', lambda: eng.set_eval(0, dirichlet_mix(eng.root_logits, worlds.valid, .25, 10), eng.root_v))
+        timed('other', lambda: eng.set_root_prior(.25, 10))
         for sim in range(1, T):
             timed('descend_expand', lambda: eng.descend_expand(sim))
             timed('net', lambda: eng.eval_leaves(cp, sim))
             timed('backup', lambda: eng.backup(sim))
             for k in launches:
                 launches[k] += 1
-        timed('other', lambda: eng.root(T))
+        timed('other', lambda: (eng.root_act(T), eng.step_and_record(True)))
         torch.cuda.synchronize()
         for kind, a, b in pairs:
             acc[kind] += a.elapsed_time(b)
@@ -335,8 +335,7 @@ def run_ours(args):
 
     def e2e_step():
         w = Hex(board=io['hb'].to(device, non_blocking=True), seats=io['hs'].to(device, non_blocking=True))
-        d = agent(w)
-        w2, tr = w.step(d.actions)
+        d, w2, tr = agent.play(w)                             # the whole move (search, action, env transition): one captured graph
         for k, src in (('actions', d.actions), ('logits', d.logits), ('v', d.v), ('board', w2.board), ('seats', w2.seats),
                        ('rewards', tr.rewards), ('terminal', tr.terminal)):
             out[k].copy_(src, non_blocking=True)

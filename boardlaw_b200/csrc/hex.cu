@@ -16,15 +16,41 @@ constexpr int NT = 128;          // envs (= threads) per CTA
 constexpr int PITCH = NT + 4;    // shared-memory pitch in elements
 
 // ---- cooperative tile movement -------------------------------------------------------------
+// 16 bytes per thread per step (the CTA's span starts at a multiple of NT*A bytes, so it is 16-byte aligned whenever the tensor
+// is), one division per 16 bytes to locate (env, cell), then incremental; unaligned tensors and the tail move byte by byte.
 __device__ __forceinline__ void tile_load(uint8_t *sb, const uint8_t *__restrict__ g, int n_bytes, int A) {
     // g points at the first env of the CTA; n_bytes = (#envs in this CTA) * A
-    for (int i = threadIdx.x; i < n_bytes; i += NT) {
+    const bool vec = (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+    const int n16 = vec ? n_bytes >> 4 : 0;
+    for (int i = threadIdx.x; i < n16; i += NT) {
+        const uint4 v = reinterpret_cast<const uint4 *>(g)[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        int e = (i * 16) / A, c = i * 16 - e * A;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            sb[c * PITCH + e] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+            if (++c == A) { c = 0; e++; }
+        }
+    }
+    for (int i = n16 * 16 + threadIdx.x; i < n_bytes; i += NT) {
         int e = i / A, c = i - e * A;
         sb[c * PITCH + e] = g[i];
     }
 }
 __device__ __forceinline__ void tile_store(const uint8_t *sb, uint8_t *__restrict__ g, int n_bytes, int A) {
-    for (int i = threadIdx.x; i < n_bytes; i += NT) {
+    const bool vec = (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+    const int n16 = vec ? n_bytes >> 4 : 0;
+    for (int i = threadIdx.x; i < n16; i += NT) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        int e = (i * 16) / A, c = i * 16 - e * A;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            w[k >> 2] |= (uint32_t)sb[c * PITCH + e] << (8 * (k & 3));
+            if (++c == A) { c = 0; e++; }
+        }
+        reinterpret_cast<uint4 *>(g)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (int i = n16 * 16 + threadIdx.x; i < n_bytes; i += NT) {
         int e = i / A, c = i - e * A;
         g[i] = sb[c * PITCH + e];
     }

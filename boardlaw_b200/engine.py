@@ -110,6 +110,14 @@ class SearchEngine:
                 self._graph_launches.pop(k, None)
             self._graph_refs.pop(old, None)
 
+    def _move_index(self):
+        return self.ws.counters[6:7].clone()
+
+    def _restore_move_index(self, saved):
+        """The reset kernel advances the device-side move counter (it keys the in-kernel random streams); warm-up and capture passes
+        must not: a search is exactly one step of the counter whether it runs eagerly, captures, or replays."""
+        self.ws.counters[6:7].copy_(saved)
+
     def release(self):
         """Drops the captured graphs (they pin the workspace and the networks' staged operands)."""
         self._graphs.clear(); self._graph_launches.clear(); self._graph_refs.clear(); self._graph_lru.clear()
@@ -242,6 +250,7 @@ class SearchEngine:
         else:
             g = self._graphs.get(gkey)
             if g is None:
+                saved = self._move_index()
                 self._move_body(cparams, c_puct, noise_eps, alpha_scale, greedy, record)        # warm-up: kernel attributes, allocations
                 g = torch.cuda.CUDAGraph()
                 before = self.launches
@@ -250,8 +259,8 @@ class SearchEngine:
                 self._graph_launches[gkey] = self.launches - before
                 self.launches = before
                 self._graphs[gkey] = g
-                self.in_board.copy_(board)                   # (the warm-up and the capture leave the inputs as they were; be explicit)
-                self.in_seats.copy_(seats)
+                self._restore_move_index(saved)
+                self.errors.zero_()                          # (the warm-up pass played the same actions: nothing to keep)
             g.replay()
             self.launches += self._graph_launches[gkey]
         self.sim = self.T
@@ -324,6 +333,7 @@ class SearchEngine:
         else:
             g = self._graphs.get(('head',) + key)
             if g is None:
+                saved = self._move_index()
                 self._reset(c_puct); self.eval_root(cparams)            # warm-up: sets kernel attributes, allocs
                 g = torch.cuda.CUDAGraph()
                 before = self.launches
@@ -333,6 +343,7 @@ class SearchEngine:
                 self._graph_launches[('head',) + key] = self.launches - before
                 self.launches = before                                   # captured, not launched
                 self._graphs[('head',) + key] = g
+                self._restore_move_index(saved)
             g.replay()
             self.launches += self._graph_launches[('head',) + key]
         valid = self.in_board.reshape(self.B, self.A) == 0
@@ -347,7 +358,9 @@ class SearchEngine:
             if g is None:
                 self._simulate_all(cparams, 1, self.T)                       # warm-up on this very tree (discarded)
                 # re-establish the state the graph expects, then capture
+                saved = self._move_index()
                 self._reset(c_puct); self.eval_root(cparams); self.set_eval(0, mixed, self.root_v)
+                self._restore_move_index(saved)
                 g = torch.cuda.CUDAGraph()
                 before = self.launches
                 with torch.cuda.graph(g):
