@@ -273,41 +273,41 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
 }
 
 // ---- backup + q-range scan ----------------------------------------------------------------------------------------
-// One CTA per group of up to 32 envs, one warp per env: the env's node records 0..sim (16 B each, contiguous) are staged in
-// shared memory with coalesced loads; then WARP 0 walks the leaf->root paths of all the CTA's envs at once, one lane per env,
-// in the staged copies (shared-memory latency per step instead of a DRAM round trip, and 32 active lanes instead of one — the
-// walk is ~60 dependent instructions per path node, which at one lane per warp made the kernel issue-bound); each warp then
-// writes its env's touched records back and the same staged records feed the (min,max) of w/(n+1e-4) that the NEXT descent
-// normalises with (slot sim+1).  Rewards are +-1 for the winner's code stored in the record's `terminal` byte (0 = not terminal).
-constexpr int BK_WARPS = 32;
-__global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int sim, int warps) {
+// Warp-local: a warp owns BK_ENVS consecutive envs.  It stages their node records 0..sim (16 B each; an env's records are
+// contiguous) in shared memory with coalesced loads, then lanes 0..BK_ENVS-1 walk their env's leaf->root path in the staged copies
+// (shared-memory latency per step instead of a DRAM round trip), then all lanes write the touched records back and scan the
+// staged records for the (min,max) of w/(n+1e-4) that the NEXT descent normalises with (slot sim+1).  No CTA barrier between the
+// phases (round 1's kernel walked all paths on warp 0 while the CTA's other seven warps sat at a __syncthreads: 12 stall cycles per
+// issue); the only block-level step is the final min/max combine.  Rewards are +-1 for the winner's code stored in the record's
+// `terminal` byte (0 = not terminal).
+constexpr int BK_WARPS = 4, BK_ENVS = 8;
+__global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int sim) {
     extern __shared__ uint4 bsm[];
     __shared__ int red[2 * BK_WARPS];
     const int T = t.T, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * warps + warp;
     const int nrec = sim + 1;                                   // node slots that can be populated so far
-    const int stride = T + ((T + 31) >> 5);                     // per env: T records, then a dirty bitmask (one word per 32 nodes)
-    uint4 *rec = bsm + (size_t)warp * stride;
-    uint32_t *dirty = reinterpret_cast<uint32_t *>(rec + T);
-    uint4 *g = reinterpret_cast<uint4 *>(t.node + (size_t)(b < t.B ? b : 0) * T);
-    // warp 0, lane l: the leaf and its value of the CTA's env l (loaded while the records travel)
+    const int b0 = (blockIdx.x * BK_WARPS + warp) * BK_ENVS;   // first env of this warp
+    uint4 *rec = bsm + (size_t)warp * BK_ENVS * (nrec + 1);    // [BK_ENVS][nrec + 1]: the odd tail word keeps the walkers on different banks
+    const int stride = nrec + 1;
+    // walkers: lane e < BK_ENVS takes env b0 + e; its leaf and leaf value travel while the records do
     int leaf = -1;
     float val[2] = {0.f, 0.f};
-    if (warp == 0 && lane < warps && blockIdx.x * warps + lane < t.B) {
-        const int bl = blockIdx.x * warps + lane;
-        leaf = t.leaf[bl];
-        const uint32_t lv = reinterpret_cast<const uint32_t *>(t.leaf_v)[bl];        // = aux[leaf].v, without the dependent load
+    if (lane < BK_ENVS && b0 + lane < t.B) {
+        leaf = t.leaf[b0 + lane];
+        const uint32_t lv = reinterpret_cast<const uint32_t *>(t.leaf_v)[b0 + lane];        // = aux[leaf].v, without the dependent load
         if (leaf >= 0) { val[0] = bl_h2f((bl_half)(lv & 0xFFFF)); val[1] = bl_h2f((bl_half)(lv >> 16)); }
     }
-    if (warp < warps && b < t.B) {
-        for (int k = lane; k < nrec; k += 32) rec[k] = g[k];
-        for (int k = lane; k < ((T + 31) >> 5); k += 32) dirty[k] = 0;
+#pragma unroll
+    for (int e = 0; e < BK_ENVS; e++) {
+        if (b0 + e < t.B) {
+            const uint4 *g = reinterpret_cast<const uint4 *>(t.node + (size_t)(b0 + e) * T);
+            for (int k = lane; k < nrec; k += 32) rec[e * stride + k] = g[k];
+        }
     }
-    __syncthreads();
+    __syncwarp();
     unsigned visited = 0;
-    if (warp == 0) {
-        uint4 *myrec = bsm + (size_t)lane * stride;
-        uint32_t *mydirty = reinterpret_cast<uint32_t *>(myrec + T);
+    if (lane < BK_ENVS) {
+        uint4 *myrec = rec + lane * stride;
         for (int cur = leaf; cur >= 0;) {
             union { uint4 u; bl_node n; } x;
             x.u = myrec[cur];
@@ -320,38 +320,46 @@ __global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int si
                 x.n.w[s] = bl_f2h(__fadd_rn(bl_h2f(x.n.w[s]), bl_h2f(bl_f2h(val[s]))));
             }
             x.n.n = (int16_t)(x.n.n + t.Sn);                    // quirk: +1 per seat (cuda.cu:228)
+            x.n.seat |= 0x80;                                   // "touched", in the staged copy only (the seat is 0 or 1)
             myrec[cur] = x.u;
-            mydirty[cur >> 5] |= 1u << (cur & 31);
             cur = x.n.parent;
             visited++;
         }
-        visited = __reduce_add_sync(0xffffffffu, visited);
     }
-    __syncthreads();
+    visited = __reduce_add_sync(0xffffffffu, visited);
+    __syncwarp();
     float lo = BL_INF, hi = -BL_INF;
-    if (warp < warps && b < t.B) {
-        for (int k = lane; k < nrec; k += 32) {
-            union { uint4 u; bl_node n; } x;
-            x.u = rec[k];
-            if ((dirty[k >> 5] >> (k & 31)) & 1u) reinterpret_cast<uint2 *>(g + k)[1] = make_uint2(x.u.z, x.u.w);   // (n, w, seat, terminal)
-            const float q0 = bl_qraw(x.n.w[0], x.n.n), q1 = bl_qraw(x.n.w[1], x.n.n);
-            lo = fminf(lo, fminf(q0, q1));
-            hi = fmaxf(hi, fmaxf(q0, q1));
+#pragma unroll
+    for (int e = 0; e < BK_ENVS; e++) {
+        if (b0 + e < t.B) {
+            uint4 *g = reinterpret_cast<uint4 *>(t.node + (size_t)(b0 + e) * T);
+            for (int k = lane; k < nrec; k += 32) {
+                union { uint4 u; bl_node n; } x;
+                x.u = rec[e * stride + k];
+                if (x.n.seat & 0x80) {
+                    x.n.seat &= 0x7F;
+                    reinterpret_cast<uint2 *>(g + k)[1] = make_uint2(x.u.z, x.u.w);   // (n, w, seat, terminal)
+                }
+                const float q0 = bl_qraw(x.n.w[0], x.n.n), q1 = bl_qraw(x.n.w[1], x.n.n);
+                lo = fminf(lo, fminf(q0, q1));
+                hi = fmaxf(hi, fmaxf(q0, q1));
+            }
         }
-        if (nrec < T) { lo = fminf(lo, 0.f); hi = fmaxf(hi, 0.f); }     // untouched slots: w = 0, n = 0 -> q = 0
     }
+    if (nrec < T) { lo = fminf(lo, 0.f); hi = fmaxf(hi, 0.f); }         // untouched slots: w = 0, n = 0 -> q = 0
     const int klo = __reduce_min_sync(0xffffffffu, bl_f2ord(lo)), khi = __reduce_max_sync(0xffffffffu, bl_f2ord(hi));
-    if (lane == 0) { red[warp] = klo; red[BK_WARPS + warp] = khi; }
+    if (lane == 0) {
+        red[warp] = klo; red[BK_WARPS + warp] = khi;
+        if (visited) atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_BACKUP_NODES), (unsigned long long)visited);
+    }
     __syncthreads();
-    if (warp == 0) {
-        const int a = __reduce_min_sync(0xffffffffu, lane < warps ? red[lane] : bl_f2ord(BL_INF));
-        const int c = __reduce_max_sync(0xffffffffu, lane < warps ? red[BK_WARPS + lane] : bl_f2ord(-BL_INF));
-        if (lane == 0) {
-            int *qr = reinterpret_cast<int *>(t.qrange) + 2 * (sim + 1);
-            atomicMin(qr, a);
-            atomicMax(qr + 1, c);
-            if (visited) atomicAdd(reinterpret_cast<unsigned long long *>(t.counters + C_BACKUP_NODES), (unsigned long long)visited);
-        }
+    if (threadIdx.x == 0) {
+        int a = red[0], c = red[BK_WARPS];
+#pragma unroll
+        for (int w = 1; w < BK_WARPS; w++) { a = min(a, red[w]); c = max(c, red[BK_WARPS + w]); }
+        int *qr = reinterpret_cast<int *>(t.qrange) + 2 * (sim + 1);
+        atomicMin(qr, a);
+        atomicMax(qr + 1, c);
     }
 }
 
@@ -559,22 +567,14 @@ extern "C" int bl_tree_backup(const bl_tree *t, int sim, bl_stream stream) {
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (sim < 1 || sim >= t->T) return -1;
-    // warps (= envs) per CTA: as many as fit in shared memory, at most BK_WARPS
-    const size_t per_warp = ((size_t)t->T + ((t->T + 31) >> 5)) * sizeof(uint4);
-    int warps = (int)(200 * 1024 / per_warp);
-    if (warps < 1) return -2;
-    if (warps > BK_WARPS) warps = BK_WARPS;
-    // envs per CTA: the phases (stage, walk, write back) are latency-bound, so small CTAs that overlap each other beat full
-    // walker warps — measured on c2: 32 envs 1.56, 16 envs 1.45, 8 envs 1.38 ms per move.  BL_BACKUP_ENVS overrides for tuning.
-    static int tune = -1;
-    if (tune < 0) { const char *e = getenv("BL_BACKUP_ENVS"); tune = e ? atoi(e) : 8; }
-    if (tune > 0 && tune < warps) warps = tune;
-    const size_t smem = per_warp * warps;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(backup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)BK_WARPS * BK_ENVS * (sim + 2) * sizeof(uint4);
+    if (smem > 226 * 1024) return -2;
+    if (smem + 256 > 48 * 1024) {                                // (the kernel's static shared memory counts towards the default limit)
+        cudaError_t e = cudaFuncSetAttribute(backup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BK_WARPS * BK_ENVS * (t->T + 1) * sizeof(uint4)));
         if (e != cudaSuccess) return (int)e;
     }
-    backup_kernel<<<(t->B + warps - 1) / warps, warps * 32, smem, bl_cu(stream)>>>(*t, sim, warps);
+    const int per_cta = BK_WARPS * BK_ENVS;
+    backup_kernel<<<(t->B + per_cta - 1) / per_cta, BK_WARPS * 32, smem, bl_cu(stream)>>>(*t, sim);
     BL_LAUNCH_CHECK();
 }
 
