@@ -17,14 +17,16 @@
 //   [256,384) activation operand, hi halves, two K elements per column (A of tcgen05.mma in "TS" form)
 //   [384,512) activation operand, lo halves (layer 0's one-hot operand has no lo part and may use both regions)
 //
-// Per-CTA roles (320 threads, 1 CTA/SM, persistent over tiles):
-//   warps 0-7  epilogue: tcgen05.ld z -> + c -> relu -> split -> tcgen05.st the next layer's operand; heads; tree I/O
-//   warp 8     weight loader: one elected thread, cp.async.bulk of host-prepacked operand tiles into a smem ring
-//   warp 9     MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=128 per half, K=16)
-// The layer's N is split in two halves and its K in two halves, issued as (h0,K0) (h1,K0) (h0,K1) (h1,K1): the epilogue of
-// half 0 runs under the MMAs of (h1,K1), the epilogue of half 1 under the next layer's (h0,K0) — the tensor pipe never
-// waits for the epilogue as long as a half-epilogue is shorter than a quarter-layer of MMAs.
-// Synchronisation is mbarrier-only between roles (weight ring full/empty, a_ready[2], acc_full[2]).
+// Per-CTA roles (448 threads, 1 CTA/SM, persistent over tiles):
+//   warps 0-7   layer group: board staging, one-hot operand, layer epilogues (tcgen05.ld z -> + c -> relu -> split -> tcgen05.st the
+//               next layer's operand)
+//   warps 8-11  heads group: masked log-softmax / tanh / tree write-back of the PREVIOUS tile, off the critical path
+//   warp 12     weight loader: one elected thread, cp.async.bulk of host-prepacked operand tiles into a smem ring
+//   warp 13     MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 (M=128, whole-N tiles, K=16)
+// A layer is issued as whole-N MMAs in K order (tc_nsplit = 1): the (N half, K half) block order that lets half-epilogues run under the
+// other half's MMAs is kept in the packer (tc_nsplit = 2) but loses, because one tcgen05.mma issue costs ~120 cycles from a single
+// thread and N = 128 instructions carry only 64 cycles of tensor work.
+// Synchronisation is mbarrier-only between roles (weight ring full/empty, a_ready, acc_full, oh_ready, heads_full, board_free[2]).
 #include "engine_internal.cuh"
 #include "hex_core.cuh"
 #include "tc_ptx.cuh"

@@ -66,3 +66,16 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, 'LIB_PATH', tmp_path / 'nope.so')
     with pytest.raises(RuntimeError, match='no CPU or PyTorch fallback'):
         _lib.lib()
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under boardlaw_b200/ imports, loads or executes oracle/ (test infrastructure), and the only shared library the product
+    opens is its own."""
+    import re
+    root = Path(__file__).resolve().parents[1] / 'boardlaw_b200'
+    for f in root.rglob('*.py'):
+        src = f.read_text()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f'{f} imports oracle'
+        assert 'oracle/' not in src and 'oracle.' not in src.replace('the oracle.', ''), f'{f} refers to oracle'
+        for m in re.finditer(r'CDLL\(([^)]*)\)', src):
+            assert 'LIB' in m.group(1) or 'libboardlaw_b200' in m.group(1), f'{f} loads {m.group(1)}'
