@@ -37,12 +37,13 @@ SOURCES = {
 }
 
 
-# Measured-and-rejected descent variants (4 = producer/consumer warps, 6 = speculative evaluation of every node):
+# Measured-and-rejected descent variants (4 = producer/consumer warps, 6 = speculative evaluation of every node, 7 = packed pass lanes + warp-cooperative visits):
 # bit-exact but slower than the default, so they stay out of the product library unless BL_EXPERIMENTAL=1 is set at build time
 # (tests/test_gpu_mcts.py and tests/test_gpu_fx.py skip them when they are not compiled in).
 EXPERIMENTAL = {
     'descend_all.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
     'descend_pc.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
+    'descend_pk.cu': ['-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false'],
 }
 if os.environ.get('BL_EXPERIMENTAL') == '1':
     del SOURCES['experimental.cu']

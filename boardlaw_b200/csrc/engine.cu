@@ -526,7 +526,11 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
     static bool env_read = false;
     if (!env_read) {                                          // BL_DESCEND_VARIANT=1|2|3 overrides the default for tuning runs
         env_read = true;
-        if (const char *e = getenv("BL_DESCEND_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 6 && ((v != 4 && v != 6) || bl_experimental_built())) g_descend_variant = v; }
+        if (const char *e = getenv("BL_DESCEND_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 7 && ((v != 4 && v != 6 && v != 7) || bl_experimental_built())) g_descend_variant = v; }
+    }
+    if (g_descend_variant == 7) {
+        const int rc = bl_descend_pk(t, sim, rands, seed, bl_cu(stream));
+        if (rc != -2 && rc != -3) return rc;                 // unsupported shape: the other kernels take it
     }
     if (g_descend_variant == 6 && t->cpi) {
         const int rc = bl_descend_all(t, sim, rands, seed, bl_cu(stream));
@@ -557,8 +561,8 @@ extern "C" int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *
 }
 
 extern "C" int bl_debug_set_descend_variant(int variant) {
-    if (variant < 0 || variant > 6) return -1;
-    if ((variant == 4 || variant == 6) && !bl_experimental_built()) return -2;     // not compiled in
+    if (variant < 0 || variant > 7) return -1;
+    if ((variant == 4 || variant == 6 || variant == 7) && !bl_experimental_built()) return -2;     // not compiled in
     g_descend_variant = variant;
     return 0;
 }

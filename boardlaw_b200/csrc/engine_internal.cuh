@@ -74,7 +74,10 @@ int64_t bl_fx_scratch_bytes(const bl_tree *t);
 // + expand + env step.  -2 = unsupported shape, -3 = scratch too small
 int bl_descend_all(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
 int64_t bl_all_scratch_bytes(const bl_tree *t);
-bool bl_experimental_built();      // variants 4 and 6 are compiled in (BL_EXPERIMENTAL=1 at build time)
+// descend_pk.cu: packed descent (variant 7): one CTA per SM, pass warps whose lanes claim ready envs + service warps that visit a
+// node warp-cooperatively; followed by expand + env step.  -2 = unsupported shape (A > 84 or T > 64)
+int bl_descend_pk(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, cudaStream_t st);
+bool bl_experimental_built();      // variants 4, 6 and 7 are compiled in (BL_EXPERIMENTAL=1 at build time)
 // descend.cu: expand + env step of the descents recorded in t.leaf / leaf_parent / leaf_action
 int bl_expand_step(const bl_tree *t, int sim, cudaStream_t st);
 // descend.cu: device buffer of the optional phase clock (NULL = off); slots 0..15 descent, 16..31 network

@@ -258,8 +258,10 @@ int bl_tree_descend_expand(const bl_tree *t, int sim, const bl_half *rands, uint
  * 6 = speculative descent (descend_all.cu; same requirements as 5): the certified evaluation of EVERY node of every tree, independently
  *     (a node's sampled action does not depend on how it was reached), then a pointer chase from the root,
  * 4 = experimental: passes and node services on different warps of a CTA (descend_pc.cu; measured slower),
+ * 7 = experimental: one CTA per SM, pass lanes that claim ready envs + warp-cooperative node visits (descend_pk.cu; A <= 84, T <= 64;
+ *     measured slower),
  * 1 = one lane per env in lock step, reference loops verbatim (engine.cu; kept as an on-device cross-check).
- * All produce identical results (tests/test_gpu_mcts.py runs the oracle comparison for each).  4 and 6 were measured slower and are
+ * All produce identical results (tests/test_gpu_mcts.py runs the oracle comparison for each).  4, 6 and 7 were measured slower and are
  * compiled in only when the library is built with BL_EXPERIMENTAL=1; without it the call returns -2 for them. */
 int bl_debug_set_descend_variant(int variant);
 

@@ -82,6 +82,7 @@ def test_descent_variants_full_batch(S, B, T, W, D):
     fx = _search(eng, worlds, net, 5, draw)
     _assert_same(ref, fx, 'variant 5 vs 2')
     _assert_same(ref, _search(eng, worlds, net, 6, draw), 'variant 6 vs 2')
+    _assert_same(ref, _search(eng, worlds, net, 7, draw), 'variant 7 (packed) vs 2')
     evals = fx['counters'][0]
     flagged = sum(fx['counters'][8:11])
     print(f'\nS{S} B{B}: {evals} evaluations, {flagged} sent to the exact path ({100 * flagged / max(evals, 1):.3f} %: stop '

@@ -111,7 +111,7 @@ class ExtremeNet:
         return r
 
 
-@pytest.mark.parametrize('variant', [6, 5, 4, 3, 2, 1])
+@pytest.mark.parametrize('variant', [7, 6, 5, 4, 3, 2, 1])
 @pytest.mark.parametrize('S,B,T,W,D,extreme', [(5, 256, 16, 32, 2, False), (9, 200, 64, 64, 4, False), (11, 70, 128, 32, 2, False),
                                                (13, 33, 32, 16, 1, False), (7, 130, 48, 32, 2, True)])
 def test_engine_stepwise_vs_oracle(S, B, T, W, D, extreme, variant):
