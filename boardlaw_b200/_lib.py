@@ -72,6 +72,8 @@ SIGNATURES = {
     'bl_reward_to_go': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
     'bl_policy_value_loss': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, P]),
     'bl_adam_step': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, P]),
+    'bl_gemm_f32_workspace_bytes': (c_int64, [c_int, c_int, c_int]),
+    'bl_gemm_f32': (c_int, [P, c_int64, c_int64, c_int, P, P, c_int64, c_int64, c_int, P, P, P, c_int64, c_int, c_int, c_int, P, c_int64, P]),
 }
 
 _lib = None

@@ -33,6 +33,7 @@ SOURCES = {
     'net_tc.cu': [],
     'net_tc_wide.cu': [],
     'learner.cu': [],
+    'gemm_tc.cu': [],
     'host.cu': [],
 }
 

@@ -280,7 +280,10 @@ __global__ void __launch_bounds__(ENT) descend_expand_kernel(bl_tree t, int sim,
 // phases (round 1's kernel walked all paths on warp 0 while the CTA's other seven warps sat at a __syncthreads: 12 stall cycles per
 // issue); the only block-level step is the final min/max combine.  Rewards are +-1 for the winner's code stored in the record's
 // `terminal` byte (0 = not terminal).
-constexpr int BK_WARPS = 4, BK_ENVS = 8;
+// BK_ENVS: 8 for trees of up to 64 nodes; 2 for larger ones, whose staged records would otherwise leave one CTA per SM (c3, T = 256:
+// 38 ms per move with 8 envs per warp against 18 for round 1's kernel).
+constexpr int BK_WARPS = 4;
+template <int BK_ENVS>
 __global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int sim) {
     extern __shared__ uint4 bsm[];
     __shared__ int red[2 * BK_WARPS];
@@ -571,14 +574,18 @@ extern "C" int bl_tree_backup(const bl_tree *t, int sim, bl_stream stream) {
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (sim < 1 || sim >= t->T) return -1;
-    const size_t smem = (size_t)BK_WARPS * BK_ENVS * (sim + 2) * sizeof(uint4);
+    const int envs = t->T <= 64 ? 8 : 2;
+    const size_t smem = (size_t)BK_WARPS * envs * (sim + 2) * sizeof(uint4);
     if (smem > 226 * 1024) return -2;
     if (smem + 256 > 48 * 1024) {                                // (the kernel's static shared memory counts towards the default limit)
-        cudaError_t e = cudaFuncSetAttribute(backup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BK_WARPS * BK_ENVS * (t->T + 1) * sizeof(uint4)));
+        const int full = (int)(BK_WARPS * envs * (t->T + 1) * sizeof(uint4));
+        cudaError_t e = envs == 8 ? cudaFuncSetAttribute(backup_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, full)
+                                  : cudaFuncSetAttribute(backup_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, full);
         if (e != cudaSuccess) return (int)e;
     }
-    const int per_cta = BK_WARPS * BK_ENVS;
-    backup_kernel<<<(t->B + per_cta - 1) / per_cta, BK_WARPS * 32, smem, bl_cu(stream)>>>(*t, sim);
+    const int per_cta = BK_WARPS * envs;
+    if (envs == 8) backup_kernel<8><<<(t->B + per_cta - 1) / per_cta, BK_WARPS * 32, smem, bl_cu(stream)>>>(*t, sim);
+    else backup_kernel<2><<<(t->B + per_cta - 1) / per_cta, BK_WARPS * 32, smem, bl_cu(stream)>>>(*t, sim);
     BL_LAUNCH_CHECK();
 }
 

@@ -23,6 +23,7 @@
 //   warp 12     weight loader (one thread): cp.async.bulk of host-prepacked weight chunks, runs ahead of the layers freely
 //   warp 13     operand loader (one thread): cp.async.bulk of the scratch strip's chunks once the layer group has published them
 //   warp 14     MMA issuer (one thread): per N half, per 16-wide K chunk {hi*hi -> acc_hh; hi*lo, lo*hi -> acc_lo}, M128 x N256 x K16
+#include <cstdlib>
 #include "engine_internal.cuh"
 #include "hex_core.cuh"
 #include "tc_ptx.cuh"
@@ -53,9 +54,35 @@ struct WideParams {
     uint8_t *scratch;                      // per CTA: two operand strips of strip_bytes() each, then all CTAs' z strips (TILE_M * W * 4)
     int B, S, A, W, D, K0p, Np, precision, nstages;
     int tree_mode;
+    int l2mode;                            // bit 0: the z strips, bit 1: the operand strips are accessed with an L2 evict_last policy (BL_WIDE_L2)
     bl_tree tree;
     unsigned long long *prof;
 };
+
+// scratch-strip accesses with an L2 eviction policy: the strips are rewritten every layer and should never reach DRAM
+__device__ __forceinline__ uint64_t wide_policy_keep() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void wide_st16(void *ptr, const uint4 &v, uint64_t pol, bool hint) {
+    if (hint) asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+    else *reinterpret_cast<uint4 *>(ptr) = v;
+}
+__device__ __forceinline__ void wide_st16_cg(void *ptr, const uint4 &v, uint64_t pol, bool hint) {
+    if (hint) asm volatile("st.global.cg.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+    else __stcg(reinterpret_cast<uint4 *>(ptr), v);
+}
+__device__ __forceinline__ uint4 wide_ld16_cg(const void *ptr, uint64_t pol, bool hint) {
+    uint4 v;
+    if (hint) asm volatile("ld.global.cg.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol) : "memory");
+    else v = __ldcg(reinterpret_cast<const uint4 *>(ptr));
+    return v;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
 
 __host__ __device__ inline int board_pitch_bytes(int A) { return 4 * (((A + 3) / 4) | 1); }
 __host__ __device__ inline size_t strip_bytes(int W, int K0p) { return (size_t)TILE_M * (W > K0p ? W : K0p) * 4; }
@@ -117,6 +144,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     const float *bh = sbias + (size_t)(D + 1) * W;                 // head bias
+    const uint64_t keep = wide_policy_keep();
+    const bool keep_z = p.l2mode & 1, keep_a = p.l2mode & 2;
 
     if (warp == WARP_LOADW) {
         // ---- weight loader: the blob is laid out in consumption order, one chunk per stage ----------------------------------
@@ -159,7 +188,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
                             if (L > 0 && h == 0 && c % (nk / (W / NI)) == 0) { mbar_wait(smem_u32(a_ready), aph); aph ^= 1; }
                             mbar_wait(smem_u32(empty + stage), ph ^ 1);
                             mbar_expect_tx(smem_u32(full_a + stage), ACT_CHUNK);
-                            bulk_g2s(smem_u32(astage0 + (size_t)ACT_CHUNK * stage), src + (size_t)c * ACT_CHUNK, ACT_CHUNK, smem_u32(full_a + stage));
+                            if (keep_a) bulk_g2s_hint(smem_u32(astage0 + (size_t)ACT_CHUNK * stage), src + (size_t)c * ACT_CHUNK, ACT_CHUNK, smem_u32(full_a + stage), keep);
+                            else bulk_g2s(smem_u32(astage0 + (size_t)ACT_CHUNK * stage), src + (size_t)c * ACT_CHUNK, ACT_CHUNK, smem_u32(full_a + stage));
                             if (++stage == p.nstages) { stage = 0; ph ^= 1; }
                         }
                 }
@@ -315,7 +345,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
                     };
                     uint4 zn4[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) zn4[j] = L > 0 ? __ldcg(zaddr(0) + j * TILE_M) : make_uint4(0, 0, 0, 0);
+                    for (int j = 0; j < 4; j++) zn4[j] = L > 0 ? wide_ld16_cg(zaddr(0) + j * TILE_M, keep, keep_z) : make_uint4(0, 0, 0, 0);
                     mbar_wait(smem_u32(acc_full), accph);
                     accph ^= 1;
                     tc_fence_after();
@@ -335,7 +365,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
                         for (int j = 0; j < 4; j++) zo[j] = zn4[j];
                         if (L > 0 && q + 1 < NI / 32) {
 #pragma unroll
-                            for (int j = 0; j < 4; j++) zn4[j] = __ldcg(zaddr(q + 1) + j * TILE_M);
+                            for (int j = 0; j < 4; j++) zn4[j] = wide_ld16_cg(zaddr(q + 1) + j * TILE_M, keep, keep_z);
                         }
                         uint32_t acc[16], acl[16];
                         tmem_wait_ld();
@@ -356,8 +386,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
                         if (L < D) {
 #pragma unroll
                             for (int j = 0; j < 4; j++)
-                                __stcg(zrow + j * TILE_M, make_uint4(__float_as_uint(zn[4 * j]), __float_as_uint(zn[4 * j + 1]),
-                                                                                        __float_as_uint(zn[4 * j + 2]), __float_as_uint(zn[4 * j + 3])));
+                                wide_st16_cg(zrow + j * TILE_M, make_uint4(__float_as_uint(zn[4 * j]), __float_as_uint(zn[4 * j + 1]),
+                                                                          __float_as_uint(zn[4 * j + 2]), __float_as_uint(zn[4 * j + 3])), keep, keep_z);
                         }
                         uint32_t hi2[8], lo2[8];
 #pragma unroll
@@ -375,9 +405,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc_tc_w
 #pragma unroll
                         for (int u = 0; u < 2; u++) {
                             uint8_t *dst = dst_strip + (size_t)(col / KC) * ACT_CHUNK + u * LBO;
-                            *reinterpret_cast<uint4 *>(dst) = make_uint4(hi2[4 * u], hi2[4 * u + 1], hi2[4 * u + 2], hi2[4 * u + 3]);
+                            wide_st16(dst, make_uint4(hi2[4 * u], hi2[4 * u + 1], hi2[4 * u + 2], hi2[4 * u + 3]), keep, keep_a);
                             if (p.precision == 0)
-                                *reinterpret_cast<uint4 *>(dst + ACT_BLOCK) = make_uint4(lo2[4 * u], lo2[4 * u + 1], lo2[4 * u + 2], lo2[4 * u + 3]);
+                                wide_st16(dst + ACT_BLOCK, make_uint4(lo2[4 * u], lo2[4 * u + 1], lo2[4 * u + 2], lo2[4 * u + 3]), keep, keep_a);
                         }
                     }
                     // the accumulators are drained: the next half's (or the heads') MMAs may overwrite them; this half of the next
@@ -585,6 +615,9 @@ int launch(const bl_fc_params *p, WideParams &k, int B, void *scratch, cudaStrea
     k.cbias = p->b_head;
     k.scratch = reinterpret_cast<uint8_t *>(scratch);
     k.prof = bl_phase_prof();
+    static int l2mode = -1;
+    if (l2mode < 0) { const char *e = getenv("BL_WIDE_L2"); l2mode = e ? atoi(e) & 3 : 0; }
+    k.l2mode = l2mode;
     k.B = B; k.S = S; k.A = A; k.W = W; k.D = p->D; k.precision = p->precision;
     k.K0p = (2 * A + KC - 1) / KC * KC;
     k.Np = (A + 1 + 31) / 32 * 32;

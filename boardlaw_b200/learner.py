@@ -1,10 +1,11 @@
 """The learner step on the self-play trajectories — ``main.as_chunk`` / ``learning.reward_to_go`` / ``main.optimize``
 (boardlaw/main.py:61-101, boardlaw/learning.py:57-76) — SURVEY.md 8 f2.
 
-Hand-written kernels (csrc/learner.cu, through the C ABI): the reward-to-go scan, the fused policy/value loss with its
-gradient, and Adam over one flat parameter buffer.  The learner's dense contractions are plain GEMMs (forward, dgrad,
-wgrad of ``FCModel``: ~3x one network launch of the self-play path per 64 moves) and go to cuBLAS through
-``torch.addmm`` / ``torch.mm``; there is no autograd graph — the backward below is the network's written out.
+Hand-written kernels (through the C ABI): the reward-to-go scan, the fused policy/value loss with its gradient, Adam over
+one flat parameter buffer (csrc/learner.cu), and the dense contractions — forward, dgrad, wgrad of ``FCModel`` — on the tcgen05
+tensor cores with fp32 accuracy (csrc/gemm_tc.cu, ``gemm`` below: split-fp16 products, fp32 accumulation in tensor memory,
+transposed operands as stride swaps, wgrad split over the sample axis).  There is no autograd graph — the backward below is the
+network's written out; the remaining torch calls are elementwise / reductions.
 Arithmetic: fp32 throughout (the reference runs this step under fp16 autocast with a GradScaler, boardlaw/main.py:88,103-106;
 fp32 is the higher-precision form of the same update).
 """
@@ -12,6 +13,41 @@ import torch
 
 from . import _lib, arrdict
 from ._lib import ptr, check
+
+
+def amax(t):
+    """max |t| as a 0-dim device tensor (one reduction, no host sync): the scale ``gemm`` brings an operand into fp16's range with."""
+    return torch.linalg.vector_norm(t, float('inf'))
+
+
+def gemm(a, b, bias=None, a_relu=False, b_relu=False, out=None, a_amax=None, b_amax=None):
+    """``op(a) @ op(b).T (+ bias)`` on the tensor cores with fp32 accuracy (csrc/gemm_tc.cu): a (M, K) and b (N, K) are 2-D fp32 CUDA
+    tensors with ANY strides (pass ``x.t()`` for a transposed operand: no copy is made); ``a_relu`` / ``b_relu`` apply relu to the
+    operand on the way in.  The kernel scales each operand into fp16's range by a power of two taken from its max |x| — ``a_amax`` /
+    ``b_amax`` (0-dim device tensors; any upper bound within a few binades works), computed here on the device when not given (no
+    host sync).  Returns (M, N) fp32, or fills ``out`` (row-major rows, any row pitch)."""
+    dev = _lib.require_cuda(a, b)
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.ndim == 2 and b.ndim == 2 and a.shape[1] == b.shape[1]
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    assert out.shape == (M, N) and out.dtype == torch.float32 and (N == 1 or out.stride(1) == 1)
+    if M == 0 or N == 0:
+        return out
+    if a_amax is None:
+        a_amax = amax(a) if K else a.new_zeros(())
+    if b_amax is None:
+        b_amax = amax(b) if K else b.new_zeros(())
+    lib = _lib.lib()
+    wsb = lib.bl_gemm_f32_workspace_bytes(M, N, K)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev) if wsb else None
+    if bias is not None:
+        bias = bias.float().contiguous()
+    check(lib.bl_gemm_f32(ptr(a), a.stride(0), a.stride(1), int(a_relu), ptr(a_amax), ptr(b), b.stride(0), b.stride(1), int(b_relu),
+                          ptr(b_amax), ptr(bias) if bias is not None else None, ptr(out), out.stride(0), M, N, K,
+                          ptr(ws) if ws is not None else None, wsb, _lib.stream_for(dev)), 'bl_gemm_f32')
+    return out
 
 
 def reward_to_go(reward, value, terminal, gamma=1., half=False):
@@ -81,16 +117,22 @@ class Learner:
         valid = worlds.valid
         body = list(net.body)
         with torch.no_grad():
-            x = torch.addmm(body[0].bias, obs, body[0].weight.t())                     # heads.py:47-52
-            xs, us = [x], []
+            obs = obs.float()
+            one = obs.new_ones(())                                                      # max |obs| (0/1 planes)
+            wv, wp = net.value.core.weight, net.policy.core.weight                      # (1, W), (A, W)
+            wmax = {id(m): amax(m.weight) for m in body}
+            wp_max, wv_max = amax(wp), amax(wv)
+            x = gemm(obs, body[0].weight, bias=body[0].bias, a_amax=one, b_amax=wmax[id(body[0])])   # heads.py:47-52
+            xs, xmax, us = [x], [amax(x)], []
             for blk in body[1:]:                                                       # networks.py:17-18
-                u = torch.addmm(blk.bias, torch.relu(x), blk.weight.t())
+                u = gemm(x, blk.weight, bias=blk.bias, a_relu=True, a_amax=xmax[-1], b_amax=wmax[id(blk)])
                 x = x + getattr(blk, 'α') * u
                 us.append(u)
                 xs.append(x)
-            scores = torch.addmm(net.policy.core.bias, x, net.policy.core.weight.t())  # heads.py:101-104
+                xmax.append(amax(x))
+            scores = gemm(x, wp, bias=net.policy.core.bias, a_amax=xmax[-1], b_amax=wp_max)          # heads.py:101-104
             logp = torch.log_softmax(scores.masked_fill(~valid, float('-inf')), -1)
-            t = torch.tanh(torch.addmv(net.value.core.bias, x, net.value.core.weight[0]))   # heads.py:136-142
+            t = torch.tanh(gemm(x, wv, bias=net.value.core.bias, a_amax=xmax[-1], b_amax=wv_max)[:, 0])   # heads.py:136-142
             seats = worlds.seats.int().contiguous()
             v = torch.where(seats[:, None] == 0, torch.stack([t, -t], -1), torch.stack([-t, t], -1)).contiguous()
 
@@ -101,21 +143,25 @@ class Learner:
             tv = _lib.proxy(batch.reward_to_go.contiguous(), torch.float16, 2, 'reward_to_go')
             check(_lib.lib().bl_policy_value_loss(ptr(logp), ptr(v), ptr(tl), ptr(tv), ptr(seats), ptr(dscores), ptr(dz), ptr(sums),
                                                   N, A, _lib.stream_for(self.device)), 'bl_policy_value_loss')
-            # backward of the network, written out
-            torch.mm(dscores.t(), x, out=g['policy.core.weight'])
+            # backward of the network, written out: wgrad = dY^T . X (both operands transposed views, split over the sample axis),
+            # dgrad = dY . W (W as a transposed view); the ReZero gate multiplies the small results, not the (N, W) operands
+            ds_max, dz_max = amax(dscores), amax(dz)
+            gemm(dscores.t(), x.t(), out=g['policy.core.weight'], a_amax=ds_max, b_amax=xmax[-1])
             g['policy.core.bias'].copy_(dscores.sum(0))
-            g['value.core.weight'].copy_((dz[None, :] @ x))
+            gemm(dz[None, :], x.t(), out=g['value.core.weight'], a_amax=dz_max, b_amax=xmax[-1])
             g['value.core.bias'].copy_(dz.sum(0, keepdim=True))
-            dx = torch.addmm(dz[:, None] * net.value.core.weight, dscores, net.policy.core.weight)
+            dx = gemm(dscores, wp.t(), a_amax=ds_max, b_amax=wp_max).addcmul_(dz[:, None], wv)
             for k in range(len(body) - 1, 0, -1):
                 blk, u, xin = body[k], us[k - 1], xs[k - 1]
                 alpha = getattr(blk, 'α')
+                dmax = amax(dx)
                 g[f'body.{k}.α'].copy_((dx * u).sum())
-                du = alpha * dx
-                torch.mm(du.t(), torch.relu(xin), out=g[f'body.{k}.weight'])
-                g[f'body.{k}.bias'].copy_(du.sum(0))
-                dx = dx + (du @ blk.weight) * (xin > 0)
-            torch.mm(dx.t(), obs, out=g['body.0.weight'])
+                gw = g[f'body.{k}.weight']
+                gemm(dx.t(), xin.t(), b_relu=True, out=gw, a_amax=dmax, b_amax=xmax[k - 1])
+                gw.mul_(alpha)
+                g[f'body.{k}.bias'].copy_(alpha * dx.sum(0))
+                dx = dx + (alpha * gemm(dx, blk.weight.t(), a_amax=dmax, b_amax=wmax[id(blk)])) * (xin > 0)
+            gemm(dx.t(), obs.t(), out=g['body.0.weight'], a_amax=amax(dx), b_amax=one)
             g['body.0.bias'].copy_(dx.sum(0))
         return -sums[0] / N, sums[1] / (2 * N)
 

@@ -341,6 +341,18 @@ int bl_policy_value_loss(const float *logp, const float *v, const bl_half *targe
 int bl_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                  float beta2, float eps, int step, bl_stream stream);
 
+/* The learner's dense contractions (forward, dgrad, wgrad of FCModel under main.optimize, boardlaw/main.py:75-101 — torch.nn.Linear
+ * GEMMs in the reference) on the tcgen05 tensor cores with fp32 accuracy (split-fp16 products, fp32 accumulation in tensor memory):
+ *     C[m*ldc + n] = sum_k a(m,k) * b(n,k) (+ bias[n]),   a(m,k) = A[m*a_rs + k*a_cs], b(n,k) = B[n*b_rs + k*b_cs]
+ * for any strides (a transposed operand is a stride swap); a_relu / b_relu apply max(.,0) to the operand on the way in.
+ * a_amax / b_amax: device scalars holding max|x| of each operand (NULL = values already within fp16's range): the operands are
+ * scaled by exact powers of two into range before the split and the result is scaled back.  Small M*N with a long K (wgrad) is split
+ * over K into partial products in `workspace` (bl_gemm_f32_workspace_bytes; without it the split is skipped) and summed in a fixed order. */
+int64_t bl_gemm_f32_workspace_bytes(int M, int N, int K);
+int bl_gemm_f32(const float *A, long long a_rs, long long a_cs, int a_relu, const float *a_amax, const float *B, long long b_rs,
+                long long b_cs, int b_relu, const float *b_amax, const float *bias, float *C, long long ldc, int M, int N, int K,
+                void *workspace, int64_t workspace_bytes, bl_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
