@@ -9,11 +9,11 @@
 // from its max |x| (a device scalar the caller provides: no host sync) — exact — and the product of the two inverse scales is applied
 // on the way out of the accumulator.
 //
-// The operands arrive as fp32, so the TMA engine cannot stage them: eight loader warps read fp32 (coalesced for either operand
+// The operands arrive as fp32, so the TMA engine cannot stage them: sixteen loader warps read fp32 (coalesced for either operand
 // orientation: K-major rows as 32-byte row pieces, MN-major as 32 consecutive rows per K), scale / relu / split in registers and write
 // 16-byte core-matrix rows of the UMMA canonical K-major layout into a 4-stage shared-memory ring (generic-proxy stores published with
-// fence.proxy.async + an mbarrier arrive per warp); one thread issues the MMAs and frees stages with tcgen05.commit; warps 0-3 read
-// the accumulator back (tcgen05.ld) and store C.  wgrad (K = the sample axis) is split over the grid's z dimension into partial
+// fence.proxy.async + an mbarrier arrive per warp); one thread issues the MMAs and frees stages with tcgen05.commit; the same
+// warps read the accumulator back (tcgen05.ld) and store C through a shared-memory transpose (row-contiguous stores).  wgrad (K = the sample axis) is split over the grid's z dimension into partial
 // products that a second kernel sums in a fixed order (deterministic).
 #include <cstdlib>
 
@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int G_BM = 128, G_BN = 256, G_KC = 32, G_STAGES = 4;
-constexpr int G_LOADERS = 8, G_THREADS = (G_LOADERS + 1) * 32;
+constexpr int G_LOADERS = 16, G_THREADS = (G_LOADERS + 1) * 32;
 constexpr uint32_t G_LBO = 128, G_SBO = (G_KC / 8) * 128;
 constexpr uint32_t G_A_BLOCK = G_BM * G_KC * 2, G_B_BLOCK = G_BN * G_KC * 2;
 constexpr uint32_t G_STAGE_BYTES = 2 * G_A_BLOCK + 2 * G_B_BLOCK;           // A hi, A lo, B hi, B lo
@@ -62,12 +62,11 @@ __device__ __forceinline__ void gemm_load_item(const float *src, long long rs, l
     }
 }
 // ... and, a chunk later, its scale / relu / split into the hi and lo core-matrix rows of the stage
-__device__ __forceinline__ void gemm_store_item(const float (&v)[8], int row, int kq, bool relu, float scale, uint8_t *blk_hi, uint8_t *blk_lo) {
+__device__ __forceinline__ void gemm_store_item(const float (&v)[8], int row, int kq, float floor, float scale, uint8_t *blk_hi, uint8_t *blk_lo) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-        float a = v[j] * scale, b = v[j + 1] * scale;
-        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        const float a = fmaxf(v[j] * scale, floor), b = fmaxf(v[j + 1] * scale, floor);     // floor = 0 (relu) or -inf
         const uint32_t h = pack_h2(a, b);
         const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&h));
         hi[j / 2] = h;
@@ -108,8 +107,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         // software-pipelined: the global loads of chunk c+1 are in flight (registers) while chunk c is converted and stored, so the
         // loaders never sit out a global-memory round trip per stage
         const bool a_kmajor = p.a_cs == 1, b_kmajor = p.b_cs == 1;
-        const int tid = threadIdx.x;                               // 0..255
-        constexpr int AI = G_BM * 4 / (G_LOADERS * 32), BI = G_BN * 4 / (G_LOADERS * 32);     // items per thread: 2 of A, up to 4 of B
+        const int tid = threadIdx.x;                               // 0..511
+        const float a_floor = p.a_relu ? 0.f : -BL_INF_F, b_floor = p.b_relu ? 0.f : -BL_INF_F;
+        constexpr int AI = G_BM * 4 / (G_LOADERS * 32), BI = G_BN * 4 / (G_LOADERS * 32);     // items per thread: 1 of A, up to 2 of B
         int arow[AI], akq[AI], brow[BI], bkq[BI];
 #pragma unroll
         for (int j = 0; j < AI; j++) {
@@ -140,10 +140,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
             mbar_wait(smem_u32(empty + stage), ph ^ 1);
             uint8_t *st = smem + (size_t)stage * G_STAGE_BYTES;
 #pragma unroll
-            for (int j = 0; j < AI; j++) gemm_store_item(buf[j], arow[j], akq[j], p.a_relu, sa, st, st + G_A_BLOCK);
+            for (int j = 0; j < AI; j++) gemm_store_item(buf[j], arow[j], akq[j], a_floor, sa, st, st + G_A_BLOCK);
 #pragma unroll
             for (int j = 0; j < BI; j++)
-                if (brow[j] >= 0) gemm_store_item(buf[AI + j], brow[j], bkq[j], p.b_relu, sb, st + 2 * G_A_BLOCK, st + 2 * G_A_BLOCK + G_B_BLOCK);
+                if (brow[j] >= 0) gemm_store_item(buf[AI + j], brow[j], bkq[j], b_floor, sb, st + 2 * G_A_BLOCK, st + 2 * G_A_BLOCK + G_B_BLOCK);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(full + stage));
@@ -181,37 +181,53 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         }
         umma_commit(smem_u32(acc_full));
     }
-    // ---- epilogue: warps 0-3, one accumulator row per thread -------------------------------------------------------------------------
-    if (warp < 4) {
+    // ---- epilogue: the sixteen loader warps — warp w reads TMEM lanes 32 (w % 4) .. (its rows), the four warps of a lane quarter take
+    //      every fourth 32-column block; a block goes through a private shared-memory tile (the ring is idle by now) so that the
+    //      global stores are row-contiguous (8 lanes = 128 B of one row) instead of 32 scattered 16-byte pieces ----------------------
+    if (warp < G_LOADERS) {
         if (nchunks > 0) { mbar_wait(smem_u32(acc_full), 0); tc_fence_after(); }
-        const int m = m0 + warp * 32 + lane;
+        const int quad = warp & 3, part = warp >> 2;               // G_LOADERS / 4 warps share a lane quarter
+        constexpr int TP = 36;                                      // tile row pitch in floats (144 B: conflict-free both ways)
+        float *tile = reinterpret_cast<float *>(smem) + (size_t)warp * 32 * TP;
         const float ia = __uint_as_float((uint32_t)(127 - ea) << 23), ib = __uint_as_float((uint32_t)(127 - eb) << 23);
-        float *dst = p.partial ? p.partial + ((size_t)blockIdx.z * p.M + (m < p.M ? m : 0)) * p.N + n0 : p.C + (size_t)(m < p.M ? m : 0) * p.ldc + n0;
-        for (int cb = 0; cb < NI; cb += 32) {
+        const int rrow = lane >> 3, c4 = (lane & 7) * 4;            // read-back role: row inside a group of 4, first of 4 columns
+        for (int cb = part * 32; cb < NI; cb += 32 * (G_LOADERS / 4)) {
             uint32_t r[32];
-            if (nchunks > 0) { tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb, r); tmem_wait_ld(); }
+            if (nchunks > 0) { tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + cb, r); tmem_wait_ld(); }
             else {
 #pragma unroll
                 for (int j = 0; j < 32; j++) r[j] = 0;
             }
-            if (m < p.M) {
-                const bool vec = cb + 32 <= nrem && ((reinterpret_cast<uintptr_t>(dst + cb) & 15) == 0);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float x[4];
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4 *>(tile + lane * TP + j) = make_float4(__uint_as_float(r[j]) * ia * ib, __uint_as_float(r[j + 1]) * ia * ib,
+                                                                                  __uint_as_float(r[j + 2]) * ia * ib, __uint_as_float(r[j + 3]) * ia * ib);
+            __syncwarp();
+            const int n = n0 + cb + c4;                             // first of my 4 columns
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && !p.partial) {
+                if (n < p.N) bv.x = p.bias[n];
+                if (n + 1 < p.N) bv.y = p.bias[n + 1];
+                if (n + 2 < p.N) bv.z = p.bias[n + 2];
+                if (n + 3 < p.N) bv.w = p.bias[n + 3];
+            }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        x[u] = __uint_as_float(r[j + u]) * ia * ib;
-                        if (p.bias && !p.partial && cb + j + u < nrem) x[u] += p.bias[n0 + cb + j + u];
-                    }
-                    if (vec) *reinterpret_cast<float4 *>(dst + cb + j) = make_float4(x[0], x[1], x[2], x[3]);
+            for (int i = 0; i < 8; i++) {
+                const int row = i * 4 + rrow, m = m0 + quad * 32 + row;
+                float4 x = *reinterpret_cast<const float4 *>(tile + row * TP + c4);
+                x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+                if (m < p.M) {
+                    float *dst = p.partial ? p.partial + ((size_t)blockIdx.z * p.M + m) * p.N + n : p.C + (size_t)m * p.ldc + n;
+                    if (n + 3 < p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) *reinterpret_cast<float4 *>(dst) = x;
                     else {
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (cb + j + u < nrem) dst[cb + j + u] = x[u];
+                        if (n < p.N) dst[0] = x.x;
+                        if (n + 1 < p.N) dst[1] = x.y;
+                        if (n + 2 < p.N) dst[2] = x.z;
+                        if (n + 3 < p.N) dst[3] = x.w;
                     }
                 }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
