@@ -241,6 +241,42 @@ def measure_config(config, precision='fp32', steps=2, warmup=3):
     return {'value': B * T / (ms / 1e3), 'unit': 'sims/s', 'ms_per_step': ms, 'steps': steps, 'workload': describe(config), 'net_precision': precision}
 
 
+def measure_learner(config='c2', steps=5):
+    """One optimiser step (Learner.optimize: forward, loss, backward on the tcgen05 GEMMs, Adam) on a chunk of the config's batch size —
+    the learner's share of the actor/learner loop (boardlaw/main.py:147-205: one step per move once the buffer is full)."""
+    import torch
+    from boardlaw_b200 import heads, arrdict
+    from boardlaw_b200.learner import Learner
+    from boardlaw_b200.networks import FCModel, synthetic_state_dict
+    S, B, T, W, D = CONFIGS[config]
+    A = S * S
+    device = torch.device('cuda', torch.cuda.current_device())
+    net = FCModel(heads.Tensor((S, S, 2)), heads.Masked(A), width=W, depth=D)
+    net.load_state_dict(synthetic_state_dict(S, W, D, seed=0))
+    net = net.to(device)
+    worlds = make_worlds(S, B, device, seed=1)
+    g = torch.Generator(device=device).manual_seed(0)
+    logits = torch.log_softmax(torch.randn((B, A), device=device, generator=g).masked_fill(~worlds.valid, float('-inf')), -1).half()
+    batch = arrdict.arrdict(worlds=worlds, decisions=arrdict.arrdict(logits=logits),
+                            reward_to_go=(torch.rand((B, 2), device=device, generator=g) * 2 - 1).half())
+    L = Learner(net, lr=1e-4)
+    for _ in range(3):
+        L.optimize(batch)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        L.optimize(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flops = 3 * 2 * B * (2 * A * W + D * W * W + W * (A + 1))
+    del L, net, batch, worlds
+    torch.cuda.empty_cache()
+    return {'ms_per_step': ms, 'samples': B, 'useful_tflops': flops / ms / 1e9, 'workload': f'Learner.optimize on {B} samples, ' + describe(config),
+            'note': 'forward, dgrad and wgrad contractions on bl_gemm_f32 (tcgen05, split-fp16, fp32-accurate); not part of `value`'}
+
+
 def run_extras(args):
     """The other BASELINE.json configs on this GPU, a few moves each (device-timed as `value`): c3, the c5 board-size sweep, and c2 with the
     reference's own GPU precision class (fp16 autocast, boardlaw/mcts/__init__.py:131-133)."""
@@ -250,6 +286,10 @@ def run_extras(args):
             out[name + ('-amp' if precision == 'amp' else '')] = measure_config(name, precision)
         except Exception as e:
             out[name] = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
+    try:
+        out['learner-c2'] = measure_learner('c2')
+    except Exception as e:
+        out['learner-c2'] = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
     return out
 
 
