@@ -495,6 +495,10 @@ int launch_v3p(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed, i
     int grid = need < occ * BL_NUM_SMS ? need : occ * BL_NUM_SMS;
     if (g_grid_limit > 0 && grid > g_grid_limit) grid = g_grid_limit;
     if ((int64_t)grid * 32 * cap * (int64_t)sizeof(ChildEntry) > t->scratch_bytes) return -3;
+    if ((long long)grid * 32 < t->B) {                          // fewer lanes than envs: the lanes pull envs from the queue, which restarts at 0
+        cudaError_t e = cudaMemsetAsync(t->counters + C_QUEUE, 0, sizeof(uint64_t), st);     // (every env resident: no queue, no memset node
+        if (e != cudaSuccess) return (int)e;                                                  //  per simulation in the captured move)
+    }
     // every env resident (one per lane) and the lane's rows big enough for a board + flood-fill stack: expand in the same kernel
     const bool fused = (long long)grid * 32 >= t->B && t->BP <= 4 * 4 * NCH;
     descend_v3_kernel<NCH, PROF><<<grid, 32, smem, st>>>(*t, sim, rands, seed, reinterpret_cast<ChildEntry *>(t->scratch), cap, g_phase_prof,
@@ -534,8 +538,6 @@ int bl_descend_v3(const bl_tree *t, int sim, const bl_half *rands, uint64_t seed
     read_gate_env();
     const int cap = child_cap(t);
     const int nch = (t->A + 3) / 4;
-    cudaError_t e = cudaMemsetAsync(t->counters + C_QUEUE, 0, sizeof(uint64_t), st);
-    if (e != cudaSuccess) return (int)e;
     int rc;
     if (nch <= 3) rc = launch_v3<3>(t, sim, rands, seed, cap, st);
     else if (nch <= 7) rc = launch_v3<7>(t, sim, rands, seed, cap, st);
