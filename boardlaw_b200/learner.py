@@ -173,20 +173,34 @@ class Learner:
                                       _lib.stream_for(self.device)), 'bl_adam_step')
         self.network._pack_key = None                 # the kernel wrote through raw pointers: restage the inference operands
 
-    def optimize(self, batch):
-        """``main.optimize``: returns arrdict(policy_loss, value_loss)."""
+    def optimize(self, batch, group=None, world=1):
+        """``main.optimize``: returns arrdict(policy_loss, value_loss).  With ``world`` > 1 the batch is this rank's SHARD of the
+        step's samples (equal shards): the gradient (and the reported losses) are averaged over the ranks with one NCCL all-reduce
+        of the flat gradient buffer, so every replica applies the update of the whole batch — the data-parallel form of the
+        reference's single learner."""
         pl, vl = self.forward_backward(batch)
+        if world > 1:
+            import torch.distributed as dist
+            losses = torch.stack([pl, vl])
+            dist.all_reduce(self.grad, group=group)
+            dist.all_reduce(losses, group=group)
+            self.grad.div_(world)
+            pl, vl = losses[0] / world, losses[1] / world
         self.apply()
         return arrdict.arrdict(policy_loss=pl, value_loss=vl)
 
 
-def chunk_from_records(records, boardsize, batch_size=None):
+def chunk_from_records(records, boardsize, batch_size=None, shard=None):
     """The learner's chunk from the all-gathered trajectory records (``selfplay.TrajectoryPool.wait()``: one (world, B, R)
     uint8 tensor per buffered move) — the same structure ``as_chunk`` builds from the actor's buffer (boardlaw/main.py:61-73,
     171-181), with the ranks' shards side by side on the env axis.  Returns (chunk, remaining records)."""
     from . import selfplay
     from .hex import Hex
-    rec = torch.stack([r.reshape(-1, r.shape[-1]) for r in records])             # (T, world*B, R)
+    if shard is not None:
+        records_view = [r[shard:shard + 1] for r in records]                       # one rank's envs only (the data-parallel learner)
+    else:
+        records_view = records
+    rec = torch.stack([r.reshape(-1, r.shape[-1]) for r in records_view])        # (T, world*B, R)
     u = selfplay.unpack_records(rec, boardsize)
     chunk = arrdict.arrdict(
         worlds=Hex(board=u.board, seats=u.seats),

@@ -2,9 +2,12 @@
 statistics and live-arena side channels: decorrelate fresh worlds with random playouts, collect ``buffer_len`` moves of
 self-play, build the chunk (reward-to-go), take one optimiser step on one (t, env) sample per env, repeat.
 
-Multi-GPU (one process per GPU under ``torchrun``): every rank plays its own shard of envs; each move's trajectory records
-are all-gathered (``selfplay.TrajectoryPool``), so every rank holds the same chunk and applies the same deterministic update
-to its replica of the network — no weight broadcast is needed.
+Multi-GPU (one process per GPU under ``torchrun``): every rank plays its own shard of envs and each move's trajectory records
+are all-gathered (``selfplay.TrajectoryPool``), so every rank holds the whole chunk.  The optimiser step is data-parallel by default
+(``learner='sharded'``): a rank runs forward / backward on ITS shard of the step's samples and the flat gradient buffer is averaged
+with one all-reduce (1.7 MB at W256 D4), so the step costs the same at any number of GPUs; ``learner='replicated'`` runs the whole
+batch on every rank instead (no gradient exchange; n_gpus times the work).  Either way every replica applies the same update to the
+same weights — no weight broadcast is needed, and ``selfplay.check_replicas`` verifies it.
 """
 import torch
 
@@ -29,7 +32,7 @@ def setup(boardsize, width, depth, nodes=64, c_puct=1 / 16, n_envs=32 * 1024, mi
 
 
 def run(boardsize, width, depth, nodes=64, c_puct=1 / 16, lr=1e-3, n_envs=32 * 1024, buffer_len=64, mix_steps=None, max_steps=1,
-        device='cuda', pool=None, seed=0, on_step=None):
+        device='cuda', pool=None, seed=0, on_step=None, learner_mode='sharded'):
     """Returns (agent, list of arrdict(policy_loss, value_loss) per optimiser step).  ``n_envs`` is per rank; ``pool`` a
     ``selfplay.TrajectoryPool`` when running under torch.distributed (None: single process)."""
     pool = pool or selfplay.TrajectoryPool()
@@ -48,8 +51,13 @@ def run(boardsize, width, depth, nodes=64, c_puct=1 / 16, lr=1e-3, n_envs=32 * 1
             records.append(pool.wait().clone())
             worlds = new_worlds
         worlds.check()                                                              # rule violations recorded on the device by Hex.step
-        chunk, records = learner.chunk_from_records(records, boardsize, n_all)    # main.py:188
-        out = L.optimize(chunk[idxs])                                              # main.py:189
+        if world_size > 1 and learner_mode == 'sharded':
+            lo = rank * n_envs                                                      # this rank's envs inside the gathered chunk
+            chunk, records = learner.chunk_from_records(records, boardsize, n_envs, shard=rank)
+            out = L.optimize(chunk[(idxs[0][lo:lo + n_envs], idxs[1][:n_envs])], group=pool.group, world=world_size)
+        else:
+            chunk, records = learner.chunk_from_records(records, boardsize, n_all)    # main.py:188
+            out = L.optimize(chunk[idxs])                                              # main.py:189
         selfplay.check_replicas(network, pool)                                      # every rank applied the same update to the same weights
         losses.append(out)
         if on_step is not None:
