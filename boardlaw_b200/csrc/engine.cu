@@ -300,12 +300,12 @@ __global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int si
         const uint32_t lv = reinterpret_cast<const uint32_t *>(t.leaf_v)[b0 + lane];        // = aux[leaf].v, without the dependent load
         if (leaf >= 0) { val[0] = bl_h2f((bl_half)(lv & 0xFFFF)); val[1] = bl_h2f((bl_half)(lv >> 16)); }
     }
-#pragma unroll
-    for (int e = 0; e < BK_ENVS; e++) {
-        if (b0 + e < t.B) {
-            const uint4 *g = reinterpret_cast<const uint4 *>(t.node + (size_t)(b0 + e) * T);
-            for (int k = lane; k < nrec; k += 32) rec[e * stride + k] = g[k];
-        }
+    // the warp's BK_ENVS x nrec records as ONE flat item list over the lanes (an env's records are contiguous, so lanes still read
+    // consecutive 16-byte records): with a loop per env, nrec = 33 cost two rounds per env — a 5 us step in the launch time at sim 32
+    const int nenv = t.B - b0 < BK_ENVS ? (t.B - b0 < 0 ? 0 : t.B - b0) : BK_ENVS, nitem = nenv * nrec;
+    for (int i = lane; i < nitem; i += 32) {
+        const int e = i / nrec, k = i - e * nrec;
+        rec[e * stride + k] = reinterpret_cast<const uint4 *>(t.node + (size_t)(b0 + e) * T)[k];
     }
     __syncwarp();
     unsigned visited = 0;
@@ -332,22 +332,19 @@ __global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int si
     visited = __reduce_add_sync(0xffffffffu, visited);
     __syncwarp();
     float lo = BL_INF, hi = -BL_INF;
-#pragma unroll
-    for (int e = 0; e < BK_ENVS; e++) {
-        if (b0 + e < t.B) {
-            uint4 *g = reinterpret_cast<uint4 *>(t.node + (size_t)(b0 + e) * T);
-            for (int k = lane; k < nrec; k += 32) {
-                union { uint4 u; bl_node n; } x;
-                x.u = rec[e * stride + k];
-                if (x.n.seat & 0x80) {
-                    x.n.seat &= 0x7F;
-                    reinterpret_cast<uint2 *>(g + k)[1] = make_uint2(x.u.z, x.u.w);   // (n, w, seat, terminal)
-                }
-                const float q0 = bl_qraw(x.n.w[0], x.n.n), q1 = bl_qraw(x.n.w[1], x.n.n);
-                lo = fminf(lo, fminf(q0, q1));
-                hi = fmaxf(hi, fmaxf(q0, q1));
-            }
+    for (int i = lane; i < nitem; i += 32) {
+        const int e = i / nrec, k = i - e * nrec;
+        union { uint4 u; bl_node n; } x;
+        x.u = rec[e * stride + k];
+        if (x.n.seat & 0x80) {
+            x.n.seat &= 0x7F;
+            reinterpret_cast<uint2 *>(t.node + (size_t)(b0 + e) * T + k)[1] = make_uint2(x.u.z, x.u.w);   // (n, w, seat, terminal)
         }
+        // w/(n+1e-4) through the branch-free exact division (divisors in [1e-4, 32768]: always in its safe range, as bl_qnorm::fast)
+        const float den = __fadd_rn((float)x.n.n, 1.e-4f);
+        const float q0 = bl_div_fast(bl_h2f(x.n.w[0]), den), q1 = bl_div_fast(bl_h2f(x.n.w[1]), den);
+        lo = fminf(lo, fminf(q0, q1));
+        hi = fmaxf(hi, fmaxf(q0, q1));
     }
     if (nrec < T) { lo = fminf(lo, 0.f); hi = fmaxf(hi, 0.f); }         // untouched slots: w = 0, n = 0 -> q = 0
     const int klo = __reduce_min_sync(0xffffffffu, bl_f2ord(lo)), khi = __reduce_max_sync(0xffffffffu, bl_f2ord(hi));
