@@ -364,80 +364,135 @@ __global__ void __launch_bounds__(BK_WARPS * 32) backup_kernel(bl_tree t, int si
 }
 
 // ---- root ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ENT) root_kernel(bl_tree t, int sim, const bl_half *__restrict__ log_lut,
-                                                   bl_half *__restrict__ logits, bl_half *__restrict__ v,
-                                                   int64_t *__restrict__ n_leaves, int64_t *__restrict__ actions,
-                                                   const float *__restrict__ uniforms, int greedy, uint64_t seed) {
-    extern __shared__ __align__(16) uint8_t raw[];
-    Smem sm = carve(raw, t.A);
-    const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-    const int A = t.A, T = t.T, Sn = t.Sn;
-    const int b = blockIdx.x * ENT + tid, bw = blockIdx.x * ENT + wbase;
-    const bool in_range = b < t.B;
-    const size_t node0 = (size_t)(in_range ? b : 0) * T;
-    float *top = sm.top + tid, *q = sm.q + tid;
-    unsigned mask = __ballot_sync(0xffffffffu, in_range);
-    for (unsigned m = mask; m; m &= m - 1) {
-        int l = __ffs(m) - 1;
-        const float *row = t.pi + ((size_t)(bw + l) * T) * t.AP;
-        for (int a = lane; a < A; a += 32) sm.top[a * FP + wbase + l] = row[a];
-    }
+// MCTS.root (boardlaw/mcts/__init__.py:142-149, root_kernel of cuda.cu:107-136) + the agent's action (mcts/__init__.py:220-221), one
+// WARP per env: the lanes share the root's actions (3 of 81 each at 9x9) for everything that is independent per action — lambda*pi,
+// the children's q (found through the env's parent_of row, one candidate node per lane), the two IEEE divisions per action and
+// Newton pass, the final probabilities / half / log table / logits store (coalesced) — and the reference's sequential sums run on two
+// lanes (S on lane 0, g on lane 1) over the terms parked in shared memory, in the reference's order: same operations, operands and
+// order as bl_newton / bl_prob, so the logits are bit-identical.  (Round 1's kernel ran the whole evaluation serially on one lane per
+// env: 230 us per move at c2.)
+constexpr int RW_WARPS = 8;
+__global__ void __launch_bounds__(RW_WARPS * 32) root_kernel(bl_tree t, int sim, const bl_half *__restrict__ log_lut,
+                                                            bl_half *__restrict__ logits, bl_half *__restrict__ v,
+                                                            int64_t *__restrict__ n_leaves, int64_t *__restrict__ actions,
+                                                            const float *__restrict__ uniforms, int greedy, uint64_t seed) {
+    extern __shared__ __align__(16) float rsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int A = t.A, T = t.T, Sn = t.Sn, AP = t.AP, TP = (T + 7) & ~7;
+    const int b = blockIdx.x * RW_WARPS + warp;
+    if (b >= t.B) return;
+    float *top = rsm + (size_t)warp * 4 * AP, *q = top + AP, *sS = q + AP, *sG = sS + AP;
+    const size_t node0 = (size_t)b * T;
+    const float *row = t.pi + node0 * AP;
+    for (int a = lane; a < AP; a += 32) { top[a] = a < A ? row[a] : 0.f; q[a] = 0.f; sS[a] = 0.f; sG[a] = 0.f; }     // (pad entries stay +0: they add nothing to the sums)
     __syncwarp();
-    if (!in_range) return;
-    for (int a = 0; a < A; a++) q[a * FP] = 0.f;
     const bl_qnorm qn(t.qrange + 2 * sim);
     const bl_node root = bl_ld_node(t.node + node0);
     const int seat = root.seat;
     int N = 0, nc = 0;
-    for (int c = root.first_child; c >= 0;) {
-        const bl_node ch = bl_ld_node(t.node + node0 + c);
-        q[ch.relation * FP] = qn(seat ? ch.w[1] : ch.w[0], ch.n);
-        N += ch.n;
-        nc++;
-        c = ch.next_sib;
+    for (int k = 1 + lane; k < sim && k < T; k += 32) {              // the root's children: nodes whose parent is node 0
+        if (t.parent_of[(size_t)b * TP + k] == 0) {
+            const bl_node ch = bl_ld_node(t.node + node0 + k);
+            q[ch.relation] = qn(seat ? ch.w[1] : ch.w[0], ch.n);
+            N += ch.n;
+            nc++;
+        }
     }
+    N = __reduce_add_sync(0xffffffffu, N);
+    nc = __reduce_add_sync(0xffffffffu, nc);
     N += A - nc;
     const float lambda = bl_lambda(bl_h2f(t.c_puct[b]), N, A);
-    for (int a = 0; a < A; a++) top[a * FP] = __fmul_rn(lambda, top[a * FP]);
-    int it;
-    const float alpha = bl_newton(top, q, FP, A, &it);
-    // probs -> half -> log -> half (MCTS.root, boardlaw/mcts/__init__.py:142-149); log through the host-libm table
-    float tot = 0.f, best = -BL_INF;
-    int arg = -1;
-    for (int a = 0; a < A; a++) {
-        const bl_half h = log_lut[bl_f2h(bl_prob(top[a * FP], q[a * FP], alpha))];
-        logits[(size_t)b * A + a] = h;
-        if (actions) {
-            // MCTSAgent.__call__ (boardlaw/mcts/__init__.py:220-221): argmax of the root policy, or a draw from Categorical(logits)
-            const float l = bl_h2f(h), w = expf(l);
-            top[a * FP] = w;                                    // (the row is dead: keep the weights for the draw)
-            tot += w;
-            if (l > best) { best = l; arg = a; }
-        }
+    __syncwarp();
+    float alpha = 0.f;                                               // newton_search's seed (cuda.cu:44-50): a maximum, order-free
+    for (int a = lane; a < A; a += 32) {
+        const float tv = __fmul_rn(lambda, top[a]);
+        top[a] = tv;
+        alpha = fmaxf(alpha, __fadd_rn(q[a], fmaxf(tv, 1.e-4f)));
     }
-    if (actions) {
-        int act = arg;
-        if (!greedy) {
-            const float u = uniforms ? uniforms[b] : ((float)(bl_philox(seed ^ (t.counters[C_MOVE] * 0x9E3779B97F4A7C15ull), (uint64_t)b, 0xAC71ull).x >> 8) + .5f) * (1.f / 16777216.f);
-            const float target = u * tot;
-            float cum = 0.f;
-            act = -1;
-            for (int a = 0; a < A; a++) {
-                const float w = top[a * FP];
-                cum += w;
-                if (w > 0.f) { act = a; if (cum >= target) break; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) alpha = fmaxf(alpha, __shfl_xor_sync(0xffffffffu, alpha, o));
+    float error = BL_INF;
+    for (int it = 0; it < 100;) {
+        for (int a = lane; a < A; a += 32) {
+            const float tv = top[a], bot = __fsub_rn(alpha, q[a]);
+            sS[a] = __fdiv_rn(tv, bot);
+            sG[a] = __fdiv_rn(-tv, __fmul_rn(bot, bot));
+        }
+        __syncwarp();
+        float acc = 0.f;
+        if (lane < 2) {                                              // the reference's order a = 0, 1, 2, ...; four terms per 128-bit load
+            const float4 *src = reinterpret_cast<const float4 *>(lane == 0 ? sS : sG);
+#pragma unroll 3
+            for (int c = 0; c < (AP >> 2); c++) {
+                const float4 x = src[c];
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, x.x), x.y), x.z), x.w);
             }
         }
-        actions[b] = act;
+        const float S = __shfl_sync(0xffffffffu, acc, 0), g = __shfl_sync(0xffffffffu, acc, 1);
+        __syncwarp();
+        it++;
+        const float new_error = __fsub_rn(S, 1.f);
+        if ((new_error < 1e-3f) || (error == new_error)) break;
+        alpha = __fsub_rn(alpha, __fdiv_rn(new_error, g));
+        error = new_error;
     }
-    const bl_aux ra = bl_ld_aux(t.aux + node0);
-    for (int s = 0; s < Sn; s++) v[(size_t)b * Sn + s] = ra.v[s];
+    // probs -> half -> log -> half (MCTS.root, boardlaw/mcts/__init__.py:142-149); log through the host-libm table
+    for (int a = lane; a < A; a += 32) {
+        const bl_half h = log_lut[bl_f2h(bl_prob(top[a], q[a], alpha))];
+        logits[(size_t)b * A + a] = h;
+        if (actions) { sS[a] = bl_h2f(h); sG[a] = expf(bl_h2f(h)); }     // (the term rows are dead: log-probabilities and weights for the draw)
+    }
+    __syncwarp();
+    if (actions) {
+        // MCTSAgent.__call__ (boardlaw/mcts/__init__.py:220-221): argmax of the root policy (the first of equal maxima), or a draw from
+        // Categorical(logits) with the weights summed in action order
+        int act;
+        if (greedy) {
+            float best = -BL_INF;
+            int arg = A;
+            for (int a = lane; a < A; a += 32)
+                if (sS[a] > best) { best = sS[a]; arg = a; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            }
+            act = arg < A ? arg : -1;
+        } else {
+            act = -1;
+            if (lane == 0) {
+                const float4 *w4 = reinterpret_cast<const float4 *>(sG);
+                float tot = 0.f;
+#pragma unroll 3
+                for (int c = 0; c < (AP >> 2); c++) { const float4 x = w4[c]; tot += x.x; tot += x.y; tot += x.z; tot += x.w; }
+                const float u = uniforms ? uniforms[b] : ((float)(bl_philox(seed ^ (t.counters[C_MOVE] * 0x9E3779B97F4A7C15ull), (uint64_t)b, 0xAC71ull).x >> 8) + .5f) * (1.f / 16777216.f);
+                const float target = u * tot;
+                float cum = 0.f;
+                bool done = false;
+                for (int c = 0; c < (AP >> 2) && !done; c++) {
+                    const float4 x = w4[c];
+                    const float w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (!done) {
+                            cum += w[j];
+                            if (w[j] > 0.f) { act = 4 * c + j; done = cum >= target; }
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0) actions[b] = act;
+    }
+    if (lane < Sn) v[(size_t)b * Sn + lane] = bl_ld_aux(t.aux + node0).v[lane];
     int leaves = 0;
-    for (int k = 1; k < T; k++) {
+    for (int k = 1 + lane; k < T; k += 32) {
         const bl_node nd = bl_ld_node(t.node + node0 + k);
         leaves += (nd.parent != -1) && (nd.first_child == -1);
     }
-    n_leaves[b] = leaves;
+    leaves = __reduce_add_sync(0xffffffffu, leaves);
+    if (lane == 0) n_leaves[b] = leaves;
 }
 
 __global__ void __launch_bounds__(256) children_dense_kernel(bl_tree t, int16_t *__restrict__ children) {
@@ -636,13 +691,13 @@ extern "C" int bl_tree_root_act(const bl_tree *t, int sim, const bl_half *log_lu
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (sim < 1 || sim > t->T || !actions) return -1;
-    size_t smem = descend_smem(t->A);
+    const size_t smem = (size_t)RW_WARPS * 4 * t->AP * sizeof(float);
     if (smem > 227 * 1024) return -2;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    root_kernel<<<(t->B + ENT - 1) / ENT, ENT, smem, bl_cu(stream)>>>(*t, sim, log_lut, logits, v, n_leaves, actions, uniforms, greedy, seed);
+    root_kernel<<<(t->B + RW_WARPS - 1) / RW_WARPS, RW_WARPS * 32, smem, bl_cu(stream)>>>(*t, sim, log_lut, logits, v, n_leaves, actions, uniforms, greedy, seed);
     BL_LAUNCH_CHECK();
 }
 
@@ -686,13 +741,13 @@ extern "C" int bl_tree_root(const bl_tree *t, int sim, const bl_half *log_lut, b
     if (int e = check_tree(t)) return e;
     if (t->B == 0) return 0;
     if (sim < 1 || sim > t->T) return -1;
-    size_t smem = descend_smem(t->A);
+    const size_t smem = (size_t)RW_WARPS * 4 * t->AP * sizeof(float);
     if (smem > 227 * 1024) return -2;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    root_kernel<<<(t->B + ENT - 1) / ENT, ENT, smem, bl_cu(stream)>>>(*t, sim, log_lut, logits, v, n_leaves, nullptr, nullptr, 0, 0ull);
+    root_kernel<<<(t->B + RW_WARPS - 1) / RW_WARPS, RW_WARPS * 32, smem, bl_cu(stream)>>>(*t, sim, log_lut, logits, v, n_leaves, nullptr, nullptr, 0, 0ull);
     BL_LAUNCH_CHECK();
 }
 
